@@ -1,0 +1,710 @@
+// qserve_b200 -- single-query (decode) attention over the INT4 / INT8 paged KV cache, the prefill
+// RoPE + KV-quantise + page-append kernel, and the padding-offset helper.
+//
+// Replaces  kernels/csrc/fused_attention/decoderMaskedMultiheadAttentionTemplate.hpp:717-2222 (decode),
+//           kernels/csrc/fused_attention/applyBiasRopeUpdateKVCache.h:94-455 (prefill append),
+//           kernels/csrc/fused_attention/input_metadata_helper.cu:11-45.
+//
+// B200 design (DESIGN.md "Decode attention"): the reference launches one CTA per *query* head and therefore streams
+// every KV head Hq/Hkv times; here one CTA owns a (sequence, KV head, context split) and serves all query heads of the
+// GQA group from a single pass over the 4-bit pages, so HBM traffic is the algorithmic minimum.  Pages are read with
+// 128-bit (K) / 64-bit (V) fully-coalesced vector loads, one 16-token chunk per warp iteration, software-prefetched one
+// chunk ahead.  Codes are expanded in registers with the exact fp16 arithmetic of the reference's dequantiser
+// (magic-number int4->fp16, then one fp16 FMA with the per-token scale and -scale*zero) directly into mma.sync
+// m16n8k16 operand fragments: the tiny (<= 8 heads) x 16-token QK^T and PV products run on the tensor pipe with fp32
+// accumulation, the softmax is an online (flash-decoding) softmax reduced with warp shuffles, and context splits are
+// merged by the last-arriving CTA.  RoPE of q/k, KV quantisation and the page append of the new token are fused in.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace qs {
+namespace {
+
+constexpr int kD = 128;          // head dim (the reference only instantiates Dh = 128, decoderMaskedMultiheadAttention.cu:352-354)
+constexpr int kAttnThreads = 128;
+constexpr int kWarps = 4;
+constexpr int kChunk = 16;       // tokens per warp iteration
+constexpr int kMaxG = 8;         // query heads per CTA (rows of the m16 tile that carry data)
+
+struct PageGeom {
+  int tokens_per_block;   // 64
+  int code_bytes;         // tokens_per_block * size_per_token = bytes of codes per page (mBytesPerSeq)
+  int num_kv_heads;
+};
+
+// ---- fp16 helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t x, uint32_t mask, uint32_t orv) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(mask), "r"(orv));  // (x & mask) | orv
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
+  return static_cast<uint32_t>(__half_as_ushort(lo)) | (static_cast<uint32_t>(__half_as_ushort(hi)) << 16);
+}
+__device__ __forceinline__ uint32_t pack_f2h2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+constexpr uint32_t kMagic = 0x64006400u;      // half2(1024, 1024)
+constexpr uint32_t kSixteenth = 0x2c002c00u;  // half2(1/16)
+constexpr uint32_t kNeg64 = 0xd400d400u;      // half2(-64)
+
+// mma.sync m16n8k16 (fp16 x fp16 -> fp32); rows 8..15 of A are zero (a1 = a3 = 0)
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint4 ldg_nc_128(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_nc_64(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// A4 quantisation parameters (Template.hpp:1243,1067): scale = half((max-min)/L), zero = half(-L*min/(max-min))
+__device__ __forceinline__ void kv_quant_params(float mx, float mn, float L, __half& s, __half& z) {
+  const float d = __fsub_rn(mx, mn);
+  s = __float2half_rn(__fdiv_rn(d, L));
+  z = __float2half_rn(__fdiv_rn(__fmul_rn(-L, mn), d));
+}
+__device__ __forceinline__ uint32_t kv_quant_code(float x, float inv_s, float z) {
+  uint32_t r;
+  const float t = __fadd_rn(__fmul_rn(x, inv_s), z);
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(t));
+  return r;
+}
+
+// per-chunk register staging of the raw page bytes
+template <int BITS>
+struct ChunkRegs {
+  // K: thread (g = lane/4, q = lane%4) holds dims [32q, 32q+32) of tokens g and 8+g
+  uint4 k[BITS == 4 ? 2 : 4];
+  // V: thread holds dims [16g, 16g+16) of tokens 2q, 2q+1, 2q+8, 2q+9
+  uint2 v4[BITS == 4 ? 4 : 1];
+  uint4 v8[BITS == 8 ? 4 : 1];
+  uint32_t ksz, vsz;  // lanes 0..15: packed (scale, aux) of token `lane` of the chunk
+};
+
+template <int BITS>
+__device__ __forceinline__ void load_chunk(ChunkRegs<BITS>& r, const long long* kptrs, const long long* vptrs, int t0, int tlen, int h,
+                                           const PageGeom& pg, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const int blk = t0 / pg.tokens_per_block;
+  const int slot0 = t0 - blk * pg.tokens_per_block;
+  const uint8_t* kpage = reinterpret_cast<const uint8_t*>(kptrs[blk]);
+  const uint8_t* vpage = reinterpret_cast<const uint8_t*>(vptrs[blk]);
+  constexpr int kRowBytes = kD * BITS / 8;
+  const uint8_t* krow = kpage + static_cast<size_t>(h * pg.tokens_per_block + slot0) * kRowBytes;
+  const uint8_t* vrow = vpage + static_cast<size_t>(h * pg.tokens_per_block + slot0) * kRowBytes;
+  if constexpr (BITS == 4) {
+    r.k[0] = ldg_nc_128(krow + g * kRowBytes + q * 16);
+    r.k[1] = ldg_nc_128(krow + (8 + g) * kRowBytes + q * 16);
+    r.v4[0] = ldg_nc_64(vrow + (2 * q) * kRowBytes + g * 8);
+    r.v4[1] = ldg_nc_64(vrow + (2 * q + 1) * kRowBytes + g * 8);
+    r.v4[2] = ldg_nc_64(vrow + (2 * q + 8) * kRowBytes + g * 8);
+    r.v4[3] = ldg_nc_64(vrow + (2 * q + 9) * kRowBytes + g * 8);
+  } else {
+    r.k[0] = ldg_nc_128(krow + g * kRowBytes + q * 32);
+    r.k[1] = ldg_nc_128(krow + g * kRowBytes + q * 32 + 16);
+    r.k[2] = ldg_nc_128(krow + (8 + g) * kRowBytes + q * 32);
+    r.k[3] = ldg_nc_128(krow + (8 + g) * kRowBytes + q * 32 + 16);
+    r.v8[0] = ldg_nc_128(vrow + (2 * q) * kRowBytes + g * 16);
+    r.v8[1] = ldg_nc_128(vrow + (2 * q + 1) * kRowBytes + g * 16);
+    r.v8[2] = ldg_nc_128(vrow + (2 * q + 8) * kRowBytes + g * 16);
+    r.v8[3] = ldg_nc_128(vrow + (2 * q + 9) * kRowBytes + g * 16);
+  }
+  // scale / zero of token (t0 + lane) for lanes 0..15; scales fp16 [Hkv][64], zeros fp16 [Hkv][64] after the codes
+  const int tl = lane & 15;
+  const __half* ks = reinterpret_cast<const __half*>(kpage + pg.code_bytes) + h * pg.tokens_per_block + slot0 + tl;
+  const __half* vs = reinterpret_cast<const __half*>(vpage + pg.code_bytes) + h * pg.tokens_per_block + slot0 + tl;
+  const int zoff = pg.num_kv_heads * pg.tokens_per_block;
+  const __half s_k = __ldg(ks), z_k = __ldg(ks + zoff), s_v = __ldg(vs), z_v = __ldg(vs + zoff);
+  if constexpr (BITS == 4) {
+    // aux = half(-float(s) * float(z))   (Utils.h:2203-2204)
+    r.ksz = pack_h2(s_k, __float2half_rn(__fmul_rn(-__half2float(s_k), __half2float(z_k))));
+    r.vsz = pack_h2(s_v, __float2half_rn(__fmul_rn(-__half2float(s_v), __half2float(z_v))));
+  } else {
+    r.ksz = pack_h2(s_k, z_k);
+    r.vsz = pack_h2(s_v, z_v);
+  }
+  // slots at or beyond tlen are unwritten (or being written by the owner CTA): force a finite (zero) dequant so that
+  // p = 0 times V can never produce NaN; their logits are masked to -inf separately
+  if (t0 + tl >= tlen) r.ksz = r.vsz = 0u;
+}
+
+// 8-bit dequant of one element: half( float(s) * (float(u) - float(z)) )   (Utils.h:2095-2107)
+__device__ __forceinline__ float deq8(uint32_t u, float s, float z) { return __fmul_rn(s, __fsub_rn(static_cast<float>(u), z)); }
+
+struct SoftmaxState {
+  float m, l;
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(kAttnThreads, 3)
+decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restrict__ k_in, const __half* __restrict__ v_in, long long q_stride,
+                        long long k_stride, long long v_stride, const long long* __restrict__ kv_pointers, const int* __restrict__ lengths,
+                        __half* __restrict__ out, int num_heads, int num_kv_heads, int max_blocks, PageGeom pg, float rotary_base, int rotary_dim,
+                        int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt) {
+  const int G = num_heads / num_kv_heads;           // query heads per kv head
+  const int gparts = (G + kMaxG - 1) / kMaxG;
+  const int hk = blockIdx.x / gparts;               // kv head
+  const int gpart = blockIdx.x - hk * gparts;
+  const int h0 = hk * G + gpart * kMaxG;            // first query head of this CTA
+  const int Gc = min(kMaxG, G - gpart * kMaxG);     // query heads handled here
+  const int b = blockIdx.y;
+  const int split = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q4 = lane & 3;
+
+  __shared__ __align__(16) __half s_q[kMaxG * kD];   // rotated q
+  __shared__ __align__(16) __half s_k[kD];           // rotated new k
+  __shared__ __align__(16) __half s_v[kD];           // new v
+  __shared__ float s_cs[kD];                         // cos | sin for the 64 frequencies
+  __shared__ float s_m[kWarps + 1][kMaxG], s_l[kWarps + 1][kMaxG];
+  __shared__ __align__(16) float s_o[kWarps][kMaxG][kD];
+  __shared__ uint32_t s_last;
+
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+
+  const int tlen = (lengths ? lengths[b] : timestep) - 1;  // tokens already in the cache (Template.hpp:901)
+  const long long* kptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 0) * max_blocks;
+  const long long* vptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 1) * max_blocks;
+
+  // ---------------- new token: load, RoPE (NeoX, position tlen), stage in shared memory ----------------
+  {
+    const int half_rot = rotary_dim / 2;
+    if (threadIdx.x < half_rot) {
+      // inv_freq = t / base^(2i/rot)   (Utils.h:1147-1152), accurate powf / sincosf
+      const float inv_freq = __fdiv_rn(static_cast<float>(tlen), powf(rotary_base, __fdiv_rn(static_cast<float>(2 * threadIdx.x), static_cast<float>(rotary_dim))));
+      float sn, cs;
+      sincosf(inv_freq, &sn, &cs);
+      s_cs[threadIdx.x] = cs;
+      s_cs[half_rot + threadIdx.x] = sn;
+    }
+    __syncthreads();
+    const __half* kg = k_in + static_cast<size_t>(b) * k_stride + static_cast<size_t>(hk) * kD;
+    const __half* vg = v_in + static_cast<size_t>(b) * v_stride + static_cast<size_t>(hk) * kD;
+    for (int idx = threadIdx.x; idx < (Gc + 1) * (kD / 2); idx += kAttnThreads) {
+      const int r = idx / (kD / 2), i = idx - r * (kD / 2);  // r == Gc -> the k row
+      const __half* src = (r < Gc) ? (q_in + static_cast<size_t>(b) * q_stride + static_cast<size_t>(h0 + r) * kD) : kg;
+      __half* dst = (r < Gc) ? (s_q + r * kD) : s_k;
+      const float x0 = __half2float(src[i]), x1 = __half2float(src[i + half_rot]);
+      const float c = s_cs[i], s = s_cs[half_rot + i];
+      dst[i] = __float2half_rn(__fsub_rn(__fmul_rn(c, x0), __fmul_rn(s, x1)));
+      dst[i + half_rot] = __float2half_rn(__fadd_rn(__fmul_rn(c, x1), __fmul_rn(s, x0)));
+    }
+    for (int i = threadIdx.x; i < kD; i += kAttnThreads) s_v[i] = vg[i];
+    for (int i = threadIdx.x + Gc * kD; i < kMaxG * kD; i += kAttnThreads) s_q[i] = __float2half_rn(0.f);
+    __syncthreads();
+  }
+
+  // ---------------- quantise + append the new K/V (one CTA per kv head: split 0, first head group) ----------------
+  const bool owner = (split == 0);
+  if (owner && gpart == 0 && warp < 2) {
+    const __half* src = (warp == 0) ? s_k : s_v;
+    const long long* ptrs = (warp == 0) ? kptrs : vptrs;
+    const float L = (BITS == 4) ? 15.f : 255.f;
+    float x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = __half2float(src[lane * 4 + j]);
+    float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), mn = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+    }
+    __half sc, zp;
+    kv_quant_params(mx, mn, L, sc, zp);
+    const float inv_s = __fdiv_rn(1.0f, __half2float(sc)), zf = __half2float(zp);
+    const int blk = tlen / pg.tokens_per_block, slot = tlen - blk * pg.tokens_per_block;
+    uint8_t* page = reinterpret_cast<uint8_t*>(ptrs[blk]);
+    uint32_t c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = kv_quant_code(x[j], inv_s, zf);
+    if constexpr (BITS == 4) {
+      const uint16_t packed = static_cast<uint16_t>((c[0] & 0xF) | ((c[1] & 0xF) << 4) | ((c[2] & 0xF) << 8) | ((c[3] & 0xF) << 12));
+      reinterpret_cast<uint16_t*>(page + static_cast<size_t>(hk * pg.tokens_per_block + slot) * (kD / 2))[lane] = packed;
+    } else {
+      reinterpret_cast<uint32_t*>(page + static_cast<size_t>(hk * pg.tokens_per_block + slot) * kD)[lane] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+    }
+    if (lane == 0) {
+      __half* meta = reinterpret_cast<__half*>(page + pg.code_bytes);
+      meta[hk * pg.tokens_per_block + slot] = sc;
+      meta[pg.num_kv_heads * pg.tokens_per_block + hk * pg.tokens_per_block + slot] = zp;
+    }
+  }
+
+  // ---------------- Q operand fragments (permuted to match the in-register dequant order) ----------------
+  // KV4: k-step 2w uses dims d0+{0,4 | 1,5}, k-step 2w+1 dims d0+{2,6 | 3,7}, d0 = 32*q4 + 8w  (nibble pairs of the lop3 trick)
+  // KV8: k-step s  uses dims d0+{0,1 | 2,3},  d0 = 32*q4 + 4s
+  uint32_t qa0[8], qa2[8];
+  {
+    const __half* qr = s_q + g * kD + 32 * q4;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      if constexpr (BITS == 4) {
+        const int d0 = 8 * (s >> 1) + 2 * (s & 1);
+        qa0[s] = pack_h2(qr[d0], qr[d0 + 4]);
+        qa2[s] = pack_h2(qr[d0 + 1], qr[d0 + 5]);
+      } else {
+        qa0[s] = pack_h2(qr[4 * s], qr[4 * s + 1]);
+        qa2[s] = pack_h2(qr[4 * s + 2], qr[4 * s + 3]);
+      }
+    }
+  }
+
+  // ---------------- stream this split's share of the cached tokens ----------------
+  const float sm_scale = rsqrtf(static_cast<float>(kD)) * 1.4426950408889634f;  // 1/sqrt(D) * log2(e)
+  const int n_chunks = (tlen + kChunk - 1) / kChunk;
+  const int cps = (n_chunks + nsplit - 1) / nsplit;
+  const int c_begin = split * cps, c_end = min(n_chunks, c_begin + cps);
+
+  float o[16][2];
+  float odummy[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j][0] = o[j][1] = 0.f;
+  float m_run = -CUDART_INF_F, l_run = 0.f;
+
+  ChunkRegs<BITS> cur, nxt;
+  int c = c_begin + warp;
+  if (c < c_end) load_chunk<BITS>(cur, kptrs, vptrs, c * kChunk, tlen, hk, pg, lane);
+  for (; c < c_end; c += kWarps) {
+    const int cn = c + kWarps;
+    if (cn < c_end) load_chunk<BITS>(nxt, kptrs, vptrs, cn * kChunk, tlen, hk, pg, lane);
+    const int t0 = c * kChunk;
+
+    // ---- S = Q K^T for 2 n-tiles of 8 tokens ----
+    float sacc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+      const uint32_t sz = __shfl_sync(0xffffffffu, cur.ksz, nt * 8 + g);
+      if constexpr (BITS == 4) {
+        const uint32_t s2 = __byte_perm(sz, 0, 0x1010), c2 = __byte_perm(sz, 0, 0x3232);
+        const uint32_t wds[4] = {cur.k[nt].x, cur.k[nt].y, cur.k[nt].z, cur.k[nt].w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t x = wds[w], top = x >> 8;
+          uint32_t e0 = h2_sub(lop3_and_or(x, 0x000f000fu, kMagic), kMagic);
+          uint32_t e1 = h2_fma(lop3_and_or(x, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+          uint32_t e2 = h2_sub(lop3_and_or(top, 0x000f000fu, kMagic), kMagic);
+          uint32_t e3 = h2_fma(lop3_and_or(top, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+          e0 = h2_fma(e0, s2, c2); e1 = h2_fma(e1, s2, c2); e2 = h2_fma(e2, s2, c2); e3 = h2_fma(e3, s2, c2);
+          mma16816(sacc[nt], qa0[2 * w], qa2[2 * w], e0, e1);
+          mma16816(sacc[nt], qa0[2 * w + 1], qa2[2 * w + 1], e2, e3);
+        }
+      } else {
+        const float sf = __half2float(__ushort_as_half(static_cast<uint16_t>(sz & 0xFFFF)));
+        const float zf = __half2float(__ushort_as_half(static_cast<uint16_t>(sz >> 16)));
+        const uint32_t wds[8] = {cur.k[2 * nt].x, cur.k[2 * nt].y, cur.k[2 * nt].z, cur.k[2 * nt].w,
+                                 cur.k[2 * nt + 1].x, cur.k[2 * nt + 1].y, cur.k[2 * nt + 1].z, cur.k[2 * nt + 1].w};
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const uint32_t x = wds[s];
+          const uint32_t b0 = pack_f2h2(deq8(x & 0xFF, sf, zf), deq8((x >> 8) & 0xFF, sf, zf));
+          const uint32_t b1 = pack_f2h2(deq8((x >> 16) & 0xFF, sf, zf), deq8(x >> 24, sf, zf));
+          mma16816(sacc[nt], qa0[s], qa2[s], b0, b1);
+        }
+      }
+    }
+    // ---- online softmax for row g (tokens t0 + nt*8 + 2*q4 + {0,1}) ----
+    float p[2][2];
+    float cmax = -CUDART_INF_F;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int t = t0 + nt * 8 + 2 * q4 + j;
+        p[nt][j] = (t < tlen) ? sacc[nt][j] * sm_scale : -CUDART_INF_F;
+        cmax = fmaxf(cmax, p[nt][j]);
+      }
+    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
+    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
+    const float m_new = fmaxf(m_run, cmax);
+    const float alpha = exp2f(m_run - m_new);
+    m_run = m_new;
+    float psum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        p[nt][j] = exp2f(p[nt][j] - m_new);
+        psum += p[nt][j];
+      }
+    l_run = l_run * alpha + psum;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      o[j][0] *= alpha;
+      o[j][1] *= alpha;
+    }
+    const uint32_t pa0 = pack_f2h2(p[0][0], p[0][1]);  // tokens 2q, 2q+1
+    const uint32_t pa2 = pack_f2h2(p[1][0], p[1][1]);  // tokens 2q+8, 2q+9
+
+    // ---- O += P V ; n-tile j <-> dims 16*g' + j of thread group g' ----
+    {
+      const uint32_t szA = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4), szB = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4 + 1);
+      const uint32_t szC = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4 + 8), szD = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4 + 9);
+      if constexpr (BITS == 4) {
+        const uint32_t s01 = __byte_perm(szA, szB, 0x5410), c01 = __byte_perm(szA, szB, 0x7632);  // (sA,sB), (cA,cB)
+        const uint32_t s89 = __byte_perm(szC, szD, 0x5410), c89 = __byte_perm(szC, szD, 0x7632);
+#pragma unroll
+        for (int ww = 0; ww < 2; ++ww) {
+          const uint32_t a = ww ? cur.v4[0].y : cur.v4[0].x, bb = ww ? cur.v4[1].y : cur.v4[1].x;
+          const uint32_t cc = ww ? cur.v4[2].y : cur.v4[2].x, dd = ww ? cur.v4[3].y : cur.v4[3].x;
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint32_t sel = static_cast<uint32_t>(kb) | (static_cast<uint32_t>(kb) << 4) | (static_cast<uint32_t>(4 + kb) << 8) |
+                                 (static_cast<uint32_t>(4 + kb) << 12);  // bytes [a_kb, a_kb, b_kb, b_kb]
+            const uint32_t m01 = __byte_perm(a, bb, sel), m89 = __byte_perm(cc, dd, sel);
+            uint32_t lo01 = h2_sub(lop3_and_or(m01, 0x000f000fu, kMagic), kMagic);
+            uint32_t hi01 = h2_fma(lop3_and_or(m01, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+            uint32_t lo89 = h2_sub(lop3_and_or(m89, 0x000f000fu, kMagic), kMagic);
+            uint32_t hi89 = h2_fma(lop3_and_or(m89, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+            lo01 = h2_fma(lo01, s01, c01); hi01 = h2_fma(hi01, s01, c01);
+            lo89 = h2_fma(lo89, s89, c89); hi89 = h2_fma(hi89, s89, c89);
+            const int j = 8 * ww + 2 * kb;
+            float acc0[4] = {o[j][0], o[j][1], odummy[0], odummy[1]};
+            mma16816(acc0, pa0, pa2, lo01, lo89);
+            o[j][0] = acc0[0]; o[j][1] = acc0[1];
+            float acc1[4] = {o[j + 1][0], o[j + 1][1], odummy[0], odummy[1]};
+            mma16816(acc1, pa0, pa2, hi01, hi89);
+            o[j + 1][0] = acc1[0]; o[j + 1][1] = acc1[1];
+          }
+        }
+      } else {
+        const float sA = __half2float(__ushort_as_half(static_cast<uint16_t>(szA & 0xFFFF))), zA = __half2float(__ushort_as_half(static_cast<uint16_t>(szA >> 16)));
+        const float sB = __half2float(__ushort_as_half(static_cast<uint16_t>(szB & 0xFFFF))), zB = __half2float(__ushort_as_half(static_cast<uint16_t>(szB >> 16)));
+        const float sC = __half2float(__ushort_as_half(static_cast<uint16_t>(szC & 0xFFFF))), zC = __half2float(__ushort_as_half(static_cast<uint16_t>(szC >> 16)));
+        const float sD = __half2float(__ushort_as_half(static_cast<uint16_t>(szD & 0xFFFF))), zD = __half2float(__ushort_as_half(static_cast<uint16_t>(szD >> 16)));
+        const uint32_t wa[4] = {cur.v8[0].x, cur.v8[0].y, cur.v8[0].z, cur.v8[0].w};
+        const uint32_t wb[4] = {cur.v8[1].x, cur.v8[1].y, cur.v8[1].z, cur.v8[1].w};
+        const uint32_t wc[4] = {cur.v8[2].x, cur.v8[2].y, cur.v8[2].z, cur.v8[2].w};
+        const uint32_t wd[4] = {cur.v8[3].x, cur.v8[3].y, cur.v8[3].z, cur.v8[3].w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int sh = 8 * (j & 3);
+          const uint32_t b0 = pack_f2h2(deq8((wa[j >> 2] >> sh) & 0xFF, sA, zA), deq8((wb[j >> 2] >> sh) & 0xFF, sB, zB));
+          const uint32_t b1 = pack_f2h2(deq8((wc[j >> 2] >> sh) & 0xFF, sC, zC), deq8((wd[j >> 2] >> sh) & 0xFF, sD, zD));
+          float acc0[4] = {o[j][0], o[j][1], odummy[0], odummy[1]};
+          mma16816(acc0, pa0, pa2, b0, b1);
+          o[j][0] = acc0[0]; o[j][1] = acc0[1];
+        }
+      }
+    }
+    if (cn < c_end) cur = nxt;
+  }
+
+  // ---------------- merge the warps (and the un-quantised new token) inside the CTA ----------------
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (q4 == 0) {
+    s_m[warp][g] = m_run;
+    s_l[warp][g] = l_run;
+  }
+  // thread (g, q4) holds row g, dims 32*q4 + 16*e + j  (e = 0,1 ; j = 0..15)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    s_o[warp][g][32 * q4 + j] = o[j][0];
+    s_o[warp][g][32 * q4 + 16 + j] = o[j][1];
+  }
+  // new token logit: fp32 dot of the rotated, un-quantised q and k  (Template.hpp:1410-1441)
+  if (owner) {
+    for (int r = warp; r < Gc; r += kWarps) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc = fmaf(__half2float(s_q[r * kD + lane * 4 + j]), __half2float(s_k[lane * 4 + j]), acc);
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+      if (lane == 0) {
+        s_m[kWarps][r] = acc * sm_scale;
+        s_l[kWarps][r] = 1.f;
+      }
+    }
+  }
+  __syncthreads();
+
+  const int d = threadIdx.x;  // one output dim per thread
+  const int nparts = kWarps + (owner ? 1 : 0);
+  float* part = nullptr;
+  if (nsplit > 1) part = ws_part + ((static_cast<size_t>(b) * num_heads + h0) * nsplit + split) * (kD + 2);
+  for (int r = 0; r < Gc; ++r) {
+    float M = -CUDART_INF_F;
+    for (int w = 0; w < nparts; ++w) M = fmaxf(M, s_m[w][r]);
+    float L = 0.f, acc = 0.f;
+    for (int w = 0; w < kWarps; ++w) {
+      const float e = (s_m[w][r] == -CUDART_INF_F) ? 0.f : exp2f(s_m[w][r] - M);
+      L += s_l[w][r] * e;
+      acc += s_o[w][r][d] * e;
+    }
+    if (owner) {
+      const float e = exp2f(s_m[kWarps][r] - M);
+      L += e;
+      acc += e * __half2float(s_v[d]);
+    }
+    if (nsplit == 1) {
+      // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
+      out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
+    } else {
+      float* pr = part + static_cast<size_t>(r) * nsplit * (kD + 2);
+      pr[d] = acc;
+      if (d == 0) {
+        pr[kD] = M;
+        pr[kD + 1] = L;
+      }
+    }
+  }
+  if (nsplit > 1) {
+    __threadfence();
+    __syncthreads();
+    uint32_t* cnt = ws_cnt + static_cast<size_t>(b) * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+      const uint32_t old = atomicAdd(cnt, 1u);
+      const bool last = (old == static_cast<uint32_t>(nsplit - 1));
+      if (last) *cnt = 0;
+      s_last = last ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int r = 0; r < Gc; ++r) {
+        const float* pr = ws_part + (static_cast<size_t>(b) * num_heads + h0 + r) * nsplit * (kD + 2);
+        float M = -CUDART_INF_F;
+        for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(pr + s * (kD + 2) + kD));
+        float L = 0.f, acc = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+          const float ms = __ldcg(pr + s * (kD + 2) + kD);
+          const float e = (ms == -CUDART_INF_F) ? 0.f : exp2f(ms - M);
+          L += __ldcg(pr + s * (kD + 2) + kD + 1) * e;
+          acc += __ldcg(pr + s * (kD + 2) + d) * e;
+        }
+        out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: prefill RoPE + KV quantise + page append: one warp per (token, query head)
+//     applyBiasRopeUpdateKVCache.h:94-455 (STORE_QKV = true, no bias, NeoX)
+// ------------------------------------------------------------------------------------------------
+template <int BITS>
+__global__ void __launch_bounds__(128) prefill_append_kernel(__half* __restrict__ qkv, const int* __restrict__ seq_lens,
+                                                             const int* __restrict__ padding_offset, const long long* __restrict__ kv_pointers,
+                                                             int num_tokens, int max_blocks, int num_heads, int num_kv_heads, int seq_len,
+                                                             PageGeom pg, float rotary_base, int rotary_dim, int max_positions) {
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int G = num_heads / num_kv_heads;
+  const int warps_per_cta = blockDim.x >> 5;
+  const long long n_work = static_cast<long long>(num_tokens) * num_heads;
+  const int n = (num_heads + 2 * num_kv_heads) * kD;
+  const int half_rot = rotary_dim / 2;
+  for (long long wi = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); wi < n_work;
+       wi += static_cast<long long>(gridDim.x) * warps_per_cta) {
+    const int token = static_cast<int>(wi / num_heads), head = static_cast<int>(wi - static_cast<long long>(token) * num_heads);
+    const int kvh = head / G;
+    const int gtok = token + (padding_offset ? padding_offset[token] : 0);
+    const int bidx = gtok / seq_len, pos = gtok - bidx * seq_len;
+    const int len = seq_lens[bidx];
+    if (pos >= len) continue;  // padded slot (cannot happen with un-padded inputs)
+    __half* qrow = qkv + static_cast<size_t>(token) * n + static_cast<size_t>(head) * kD;
+    __half* krow = qkv + static_cast<size_t>(token) * n + static_cast<size_t>(num_heads + kvh) * kD;
+    __half* vrow = qkv + static_cast<size_t>(token) * n + static_cast<size_t>(num_heads + num_kv_heads + kvh) * kD;
+    const bool kv_writer = (head == kvh * G);
+    // lane handles rotary pairs i = 2*lane, 2*lane+1  (i in [0, 64)) -> dims i and i + half_rot
+    float kx[4];  // rotated k: dims 2l, 2l+1, 64+2l, 65+2l
+    float vx[4];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * lane + e;
+      float cs, sn;
+      const bool rot = true;  // rotary_dim == head_dim (update_kv_cache.cu:54)
+      const float inv_freq = __fdiv_rn(static_cast<float>(pos), powf(rotary_base, __fdiv_rn(static_cast<float>(2 * i), static_cast<float>(rotary_dim))));
+      sincosf(inv_freq, &sn, &cs);
+      const int i1 = i + half_rot;
+      const float q0 = __half2float(qrow[i]), q1 = __half2float(qrow[i1]);
+      if (rot) {
+        qrow[i] = __float2half_rn(__fsub_rn(__fmul_rn(cs, q0), __fmul_rn(sn, q1)));
+        qrow[i1] = __float2half_rn(__fadd_rn(__fmul_rn(cs, q1), __fmul_rn(sn, q0)));
+      }
+      if (kv_writer) {
+        const float k0 = __half2float(krow[i]), k1 = __half2float(krow[i1]);
+        __half r0 = krow[i], r1 = krow[i1];
+        if (rot) {
+          r0 = __float2half_rn(__fsub_rn(__fmul_rn(cs, k0), __fmul_rn(sn, k1)));
+          r1 = __float2half_rn(__fadd_rn(__fmul_rn(cs, k1), __fmul_rn(sn, k0)));
+          krow[i] = r0;
+          krow[i1] = r1;
+        }
+        kx[e] = __half2float(r0);
+        kx[2 + e] = __half2float(r1);
+        vx[e] = __half2float(vrow[i]);
+        vx[2 + e] = __half2float(vrow[i1]);
+      }
+    }
+    if (!kv_writer || kv_pointers == nullptr) continue;
+    if (pos < max(len - max_positions, 0)) continue;  // outside the cyclic window (:268-271)
+    const int blk = pos / pg.tokens_per_block, slot = pos - blk * pg.tokens_per_block;
+    const float L = (BITS == 4) ? 15.f : 255.f;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const float* x = which ? vx : kx;
+      float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), mn = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+      }
+      __half sc, zp;
+      kv_quant_params(mx, mn, L, sc, zp);
+      const float inv_s = __fdiv_rn(1.0f, __half2float(sc)), zf = __half2float(zp);
+      uint8_t* page = reinterpret_cast<uint8_t*>(kv_pointers[(static_cast<size_t>(bidx) * 2 + which) * max_blocks + blk]);
+      const uint32_t c0 = kv_quant_code(x[0], inv_s, zf), c1 = kv_quant_code(x[1], inv_s, zf);
+      const uint32_t c2 = kv_quant_code(x[2], inv_s, zf), c3 = kv_quant_code(x[3], inv_s, zf);
+      if constexpr (BITS == 4) {
+        uint8_t* row = page + static_cast<size_t>(kvh * pg.tokens_per_block + slot) * (kD / 2);
+        row[lane] = static_cast<uint8_t>((c0 & 0xF) | ((c1 & 0xF) << 4));        // dims 2l, 2l+1
+        row[32 + lane] = static_cast<uint8_t>((c2 & 0xF) | ((c3 & 0xF) << 4));   // dims 64+2l, 65+2l
+      } else {
+        uint8_t* row = page + static_cast<size_t>(kvh * pg.tokens_per_block + slot) * kD;
+        reinterpret_cast<uint16_t*>(row)[lane] = static_cast<uint16_t>(c0 | (c1 << 8));
+        reinterpret_cast<uint16_t*>(row + 64)[lane] = static_cast<uint16_t>(c2 | (c3 << 8));
+      }
+      if (lane == 0) {
+        __half* meta = reinterpret_cast<__half*>(page + pg.code_bytes);
+        meta[kvh * pg.tokens_per_block + slot] = sc;
+        meta[pg.num_kv_heads * pg.tokens_per_block + kvh * pg.tokens_per_block + slot] = zp;
+      }
+    }
+  }
+}
+
+__global__ void padding_offsets_kernel(int* __restrict__ out, const int* __restrict__ cu_seqlens, int max_seqlen) {
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const int b = blockIdx.x;
+  const int beg = cu_seqlens[b], end = cu_seqlens[b + 1];
+  const int off = b * max_seqlen - beg;
+  for (int t = beg + threadIdx.x; t < end; t += blockDim.x) out[t] = off;
+}
+
+template <typename Kern, typename... Args>
+int launch_pdl(Kern kern, dim3 grid, dim3 block, void* stream, const char* what, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, args...), what);
+}
+
+constexpr size_t kAttnCounterBytes = 256 * 1024;  // 65536 (sequence, head-group) counters
+
+}  // namespace
+
+size_t attention_workspace_bytes(int batch, int num_heads, int head_dim, int max_splits) {
+  return kAttnCounterBytes + static_cast<size_t>(batch) * num_heads * max_splits * (head_dim + 2) * sizeof(float);
+}
+
+int decode_attention(const DecodeAttnArgs& a) {
+  if (a.batch == 0) return QS_OK;
+  QS_REQUIRE(a.head_dim == kD, "single_query_attention: head_dim=%d, only 128 is supported (as in the reference)", a.head_dim);
+  QS_REQUIRE(a.kv_zeros, "single_query_attention: only kv_cache_with_zeros=True is supported (arg_utils.py:422 always sets it)");
+  QS_REQUIRE(a.num_kv_heads > 0 && a.num_heads % a.num_kv_heads == 0, "single_query_attention: heads %d / kv heads %d", a.num_heads, a.num_kv_heads);
+  QS_REQUIRE(a.tokens_per_block > 0 && a.tokens_per_block % kChunk == 0, "single_query_attention: tokens_per_block=%d must be a multiple of %d",
+             a.tokens_per_block, kChunk);
+  QS_REQUIRE(a.rotary_dim == kD, "single_query_attention: rotary_dim=%d must equal head_dim (llama_w4a8_unpad.py:258)", a.rotary_dim);
+  const int bits = a.int4_kv ? 4 : 8;
+  QS_REQUIRE(a.size_per_token == a.num_kv_heads * kD * bits / 8, "single_query_attention: size_per_token=%d does not match %d kv heads x %d bits",
+             a.size_per_token, a.num_kv_heads, bits);
+  QS_REQUIRE(a.batch <= 65535, "single_query_attention: batch=%d too large", a.batch);
+  PageGeom pg{a.tokens_per_block, a.tokens_per_block * a.size_per_token, a.num_kv_heads};
+  const int G = a.num_heads / a.num_kv_heads;
+  const int gparts = (G + kMaxG - 1) / kMaxG;
+  const int gx = a.num_kv_heads * gparts;
+  // context splits: enough CTAs to fill the machine (4 resident CTAs per SM), never more than one split per 256 tokens
+  int nsplit = 1;
+  const int ctas = gx * a.batch;
+  const int slots = 148 * 4;
+  if (ctas < slots && a.timestep > 512) {
+    nsplit = (slots + ctas - 1) / ctas;
+    const int cap = (a.timestep + 255) / 256;
+    if (nsplit > cap) nsplit = cap;
+    if (nsplit > 32) nsplit = 32;
+  }
+  float* part = nullptr;
+  uint32_t* cnt = nullptr;
+  if (nsplit > 1) {
+    const size_t need = attention_workspace_bytes(a.batch, a.num_heads, kD, nsplit);
+    if (a.workspace == nullptr || need > a.workspace_bytes || static_cast<size_t>(a.batch) * gx * 4 > kAttnCounterBytes) {
+      nsplit = 1;
+    } else {
+      cnt = static_cast<uint32_t*>(a.workspace);
+      part = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + kAttnCounterBytes);
+    }
+  }
+  dim3 grid(gx, a.batch, nsplit);
+  auto run = [&](auto kern) {
+    return launch_pdl(kern, grid, dim3(kAttnThreads), a.stream, "single_query_attention", static_cast<const __half*>(a.q),
+                      static_cast<const __half*>(a.k), static_cast<const __half*>(a.v), a.q_stride, a.k_stride, a.v_stride, a.kv_pointers, a.lengths,
+                      static_cast<__half*>(a.out), a.num_heads, a.num_kv_heads, a.max_blocks, pg, a.rotary_base, a.rotary_dim, a.timestep, nsplit,
+                      part, cnt);
+  };
+  return a.int4_kv ? run(decode_attention_kernel<4>) : run(decode_attention_kernel<8>);
+}
+
+int prefill_rope_append(const PrefillAppendArgs& a) {
+  if (a.num_tokens == 0) return QS_OK;
+  QS_REQUIRE(a.head_dim == kD, "apply_bias_rope_update_kv_cache: head_dim=%d, only 128 is supported", a.head_dim);
+  QS_REQUIRE(a.kv_zeros, "apply_bias_rope_update_kv_cache: only kv_cache_with_zeros=True is supported");
+  QS_REQUIRE(a.num_kv_heads > 0 && a.num_heads % a.num_kv_heads == 0, "apply_bias_rope_update_kv_cache: heads %d / kv heads %d", a.num_heads, a.num_kv_heads);
+  QS_REQUIRE(a.rotary_dim == kD, "apply_bias_rope_update_kv_cache: rotary_dim=%d must equal head_dim (update_kv_cache.cu:54)", a.rotary_dim);
+  QS_REQUIRE(a.seq_len > 0, "apply_bias_rope_update_kv_cache: seq_len=%d", a.seq_len);
+  const int bits = a.int4_kv ? 4 : 8;
+  QS_REQUIRE(a.size_per_token == a.num_kv_heads * kD * bits / 8, "apply_bias_rope_update_kv_cache: size_per_token=%d does not match", a.size_per_token);
+  PageGeom pg{a.tokens_per_block, a.tokens_per_block * a.size_per_token, a.num_kv_heads};
+  const long long work = static_cast<long long>(a.num_tokens) * a.num_heads;
+  long long blocks = (work + 3) / 4;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  auto run = [&](auto kern) {
+    return launch_pdl(kern, dim3(static_cast<unsigned>(blocks)), dim3(128), a.stream, "apply_bias_rope_update_kv_cache", static_cast<__half*>(a.qkv),
+                      a.seq_lens, a.padding_offset, a.kv_pointers, a.num_tokens, a.max_blocks, a.num_heads, a.num_kv_heads, a.seq_len, pg,
+                      a.rotary_base, a.rotary_dim, a.max_positions);
+  };
+  return a.int4_kv ? run(prefill_append_kernel<4>) : run(prefill_append_kernel<8>);
+}
+
+int padding_offsets(int* out, const int* cu_seqlens, int batch, int max_seqlen, void* stream) {
+  if (batch == 0) return QS_OK;
+  return launch_pdl(padding_offsets_kernel, dim3(batch), dim3(256), stream, "compute_padding_offsets", out, cu_seqlens, max_seqlen);
+}
+
+}  // namespace qs

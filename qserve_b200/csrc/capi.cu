@@ -1,0 +1,196 @@
+// qserve_b200 -- extern "C" entry points (include/qserve_b200.h) and error plumbing.
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/qserve_b200.h"
+#include "common.cuh"
+#include "launch.h"
+
+namespace qs {
+
+static thread_local char g_err[1024] = "";
+static int g_pdl = 1;
+static int g_force_upc = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return QS_OK;
+  cudaGetLastError();  // clear the sticky launch error
+  return set_error(QS_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+bool pdl_enabled() { return g_pdl != 0; }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace qs
+
+using namespace qs;
+
+extern "C" {
+
+int qs_abi_version(void) { return QS_ABI_VERSION; }
+const char* qs_last_error(void) { return g_err; }
+int qs_set_pdl(int enabled) {
+  const int old = g_pdl;
+  g_pdl = enabled ? 1 : 0;
+  return old;
+}
+int qs_gemm_force_units_per_cta(int units) {
+  const int old = g_force_upc;
+  g_force_upc = units;
+  return old;
+}
+size_t qs_gemm_workspace_bytes(void) { return gemm_workspace_bytes(); }
+
+int qs_w4a8_gemm_per_chn(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales, const void* w_szs,
+                         const void* a_ssums, void* out_feats, int32_t* acc_out, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  QS_REQUIRE(in_feats && kernel && wscales && ascales && w_szs && a_ssums && out_feats, "qgemm_w4a8_per_chn: null tensor");
+  GemmArgs a;
+  a.act = in_feats; a.weight = kernel; a.wscales = wscales; a.ascales = ascales; a.w_szs = w_szs; a.a_ssums = a_ssums;
+  a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_units_per_cta = g_force_upc; a.stream = stream;
+  return gemm_w4a8_per_chn(a);
+}
+
+int qs_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const int8_t* zeros, const int8_t* scales_i8, const void* wscales,
+                           const void* ascales, void* out_feats, int32_t* acc_out, int M, int N, int K, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  QS_REQUIRE(in_feats && kernel && zeros && scales_i8 && wscales && ascales && out_feats, "qgemm_w4a8_per_group: null tensor");
+  QS_REQUIRE(aligned16(zeros) && aligned16(scales_i8), "qgemm_w4a8_per_group: level-2 scale/zero tensors must be 16-byte aligned");
+  GemmArgs a;
+  a.act = in_feats; a.weight = kernel; a.s2_zeros = zeros; a.s2_scales = scales_i8; a.wscales = wscales; a.ascales = ascales;
+  a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_units_per_cta = g_force_upc; a.stream = stream;
+  return gemm_w4a8_per_group(a);
+}
+
+int qs_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales, void* out_feats, int32_t* acc_out,
+                 int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream) {
+  QS_REQUIRE(in_feats && kernel && wscales && ascales && out_feats, "qgemm_w8a8: null tensor");
+  GemmArgs a;
+  a.act = in_feats; a.weight = kernel; a.wscales = wscales; a.ascales = ascales;
+  a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_units_per_cta = g_force_upc; a.stream = stream;
+  return gemm_w8a8(a);
+}
+
+size_t qs_attention_workspace_bytes(int batch, int num_heads, int head_dim) { return attention_workspace_bytes(batch, num_heads, head_dim, 32); }
+
+int qs_single_query_attention(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride, int64_t v_stride,
+                              const int64_t* kv_pointers, const int32_t* length_per_sample, void* out, int batch, int num_heads,
+                              int num_kv_heads, int head_dim, int max_blocks_per_seq, int memory_max_seqlen, int tokens_per_block,
+                              int size_per_token, int timestep, int rotary_embedding_dim, float rotary_base, int neox_rotary_style,
+                              int int4_kv_cache, int kv_cache_with_zeros, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)neox_rotary_style;  // accepted and ignored: NeoX is hard-wired in the reference as well (fused_attention.cpp:109)
+  QS_REQUIRE(q && k && v && kv_pointers && out, "single_query_attention: null tensor");
+  DecodeAttnArgs a;
+  a.q = q; a.k = k; a.v = v; a.q_stride = q_stride; a.k_stride = k_stride; a.v_stride = v_stride;
+  a.kv_pointers = reinterpret_cast<const long long*>(kv_pointers); a.lengths = length_per_sample; a.out = out;
+  a.batch = batch; a.num_heads = num_heads; a.num_kv_heads = num_kv_heads; a.head_dim = head_dim; a.max_blocks = max_blocks_per_seq;
+  a.tokens_per_block = tokens_per_block; a.size_per_token = size_per_token; a.timestep = timestep; a.memory_max_len = memory_max_seqlen;
+  a.rotary_dim = rotary_embedding_dim; a.rotary_base = rotary_base; a.int4_kv = int4_kv_cache; a.kv_zeros = kv_cache_with_zeros;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.stream = stream;
+  return decode_attention(a);
+}
+
+int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens, const int32_t* padding_offset, const int64_t* kv_pointers, int batch,
+                                       int num_tokens, int max_blocks_per_seq, int head_num, int kv_head_num, int head_dim, int seq_len,
+                                       int tokens_per_block, int size_per_token, int rotary_embedding_dim, float rotary_embedding_base,
+                                       int rotary_embedding_max_positions, int neox_rotary_style, int int4_kv_cache, int kv_cache_with_zeros,
+                                       void* stream) {
+  (void)neox_rotary_style;
+  QS_REQUIRE(qkv && seq_lens, "apply_bias_rope_update_kv_cache: null tensor");
+  PrefillAppendArgs a;
+  a.qkv = qkv; a.seq_lens = seq_lens; a.padding_offset = padding_offset; a.kv_pointers = reinterpret_cast<const long long*>(kv_pointers);
+  a.batch = batch; a.num_tokens = num_tokens; a.max_blocks = max_blocks_per_seq; a.num_heads = head_num; a.num_kv_heads = kv_head_num;
+  a.head_dim = head_dim; a.seq_len = seq_len; a.tokens_per_block = tokens_per_block; a.size_per_token = size_per_token;
+  a.rotary_dim = rotary_embedding_dim; a.rotary_base = rotary_embedding_base; a.max_positions = rotary_embedding_max_positions;
+  a.int4_kv = int4_kv_cache; a.kv_zeros = kv_cache_with_zeros; a.stream = stream;
+  return prefill_rope_append(a);
+}
+
+int qs_compute_padding_offsets(int32_t* out, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream) {
+  QS_REQUIRE(out && cu_seqlens, "compute_padding_offsets: null tensor");
+  return padding_offsets(out, cu_seqlens, batch, max_seqlen, stream);
+}
+
+int qs_rms_norm(void* out, const void* input, const void* weight, float epsilon, int use_quant, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && input && weight, "rms_norm: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input) && aligned16(weight), "rms_norm: tensors must be 16-byte aligned");
+  return rms_norm(out, input, weight, epsilon, use_quant, tokens, hidden, stream);
+}
+
+int qs_rms_norm_general(int8_t* out, const void* input, const void* weight, void* scaling, float epsilon, int use_per_token_quant, int tokens,
+                        int hidden, void* stream) {
+  QS_REQUIRE(out && input && weight && scaling, "rms_norm_general: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input) && aligned16(weight), "rms_norm_general: tensors must be 16-byte aligned");
+  return layernorm_general_quant(out, input, weight, nullptr, scaling, epsilon, tokens, hidden, use_per_token_quant, stream);
+}
+
+int qs_rms_norm_general_fuse_sum(int8_t* out, const void* input, const void* weight, void* input_sum, void* scaling, float epsilon,
+                                 int use_per_token_quant, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && input && weight && scaling && input_sum, "rms_norm_general_fuse_sum: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input) && aligned16(weight), "rms_norm_general_fuse_sum: tensors must be 16-byte aligned");
+  return layernorm_general_quant(out, input, weight, input_sum, scaling, epsilon, tokens, hidden, use_per_token_quant, stream);
+}
+
+int qs_dequant_add_residual_rms_norm_quant(int8_t* out, const int32_t* input, void* residual, const void* gamma, const void* scale_vec,
+                                           float scale, float epsilon, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && input && residual && gamma, "invoke_dequant_add_residual_rms_norm_quant: null tensor");
+  return dequant_add_residual_rms_norm_quant(out, input, residual, gamma, scale_vec, scale, epsilon, tokens, hidden, stream);
+}
+
+int qs_invoke_quant(int8_t* out, const void* input, void* scale, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && input && scale, "invoke_quant: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input), "invoke_quant: tensors must be 16-byte aligned");
+  return quant_per_token(out, input, nullptr, scale, tokens, hidden, stream);
+}
+int qs_invoke_quant_scalar(int8_t* out, const void* input, float scale, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && input, "invoke_quant: null tensor");
+  return quant_scalar(out, input, scale, tokens, hidden, stream);
+}
+int qs_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_sum, void* scale, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && input && scale && input_sum, "invoke_quant_fuse_sum: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input), "invoke_quant_fuse_sum: tensors must be 16-byte aligned");
+  return quant_per_token(out, input, input_sum, scale, tokens, hidden, stream);
+}
+int qs_invoke_dequant_add_residual(void* out, const int32_t* input, const void* residual, const void* scale_vec, float scale, int tokens,
+                                   int hidden, void* stream) {
+  QS_REQUIRE(out && input && residual, "invoke_dequant_add_residual: null tensor");
+  return dequant_add_residual(out, input, residual, scale_vec, scale, tokens, hidden, stream);
+}
+int qs_invoke_dequant(void* out, const int32_t* input, float scale, int tokens, int hidden, int input_stride, int out_stride, void* stream) {
+  QS_REQUIRE(out && input, "invoke_dequant: null tensor");
+  return dequant(out, input, scale, tokens, hidden, input_stride, out_stride, stream);
+}
+
+int qs_silu_and_mul(void* out, const void* input, int tokens, int d, void* stream) {
+  QS_REQUIRE(out && input, "silu_and_mul: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input), "silu_and_mul: tensors must be 16-byte aligned");
+  return silu_and_mul(out, input, tokens, d, stream);
+}
+int qs_gelu_new(void* out, const void* input, int tokens, int d, void* stream) {
+  QS_REQUIRE(out && input, "gelu_new: null tensor");
+  return gelu(out, input, tokens, d, 0, stream);
+}
+int qs_gelu_fast(void* out, const void* input, int tokens, int d, void* stream) {
+  QS_REQUIRE(out && input, "gelu_fast: null tensor");
+  return gelu(out, input, tokens, d, 1, stream);
+}
+int qs_dequant_silu_and_mul_quant(int8_t* out, const int32_t* input, float scale_gate, float scale_up, float scale_out, float* scale_out_vec,
+                                  float* tmp, int tokens, int d, void* stream) {
+  QS_REQUIRE(out && input, "invoke_dequant_silu_and_mul_quant: null tensor");
+  QS_REQUIRE((scale_out_vec == nullptr) == (tmp == nullptr), "invoke_dequant_silu_and_mul_quant: scale_out and tmp must be given together");
+  return dequant_silu_and_mul_quant(out, input, scale_gate, scale_up, scale_out, scale_out_vec, tmp, tokens, d, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+// qserve_b200 -- fused norm / activation / per-token INT8 quantisation kernels (fp16 activations).
+//
+// Replaces kernels/csrc/layernorm_kernels.cu, fused_kernels.cu, activation_kernels.cu of the reference.
+// Each op reads its row from HBM exactly once (row cached in shared memory as fp16), uses 128-bit vector
+// accesses, IEEE fp32 arithmetic in the reference's source order, and is PDL-aware (griddepcontrol.wait /
+// launch_dependents) so back-to-back launches of the decode step overlap their prologues.
+#include "common.cuh"
+#include "launch.h"
+
+namespace qs {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ int8_t cvt_s8(float x) {
+  int32_t r;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return static_cast<int8_t>(r);
+}
+
+template <typename Op>
+__device__ __forceinline__ float warp_reduce(float v, Op op) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+struct OpSum { __device__ float operator()(float a, float b) const { return a + b; } };
+struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+
+// block-wide all-reduce for kThreads threads; red must hold >= 32 floats; result broadcast to all threads
+template <typename Op>
+__device__ __forceinline__ float block_reduce(float v, float* red, Op op, float identity) {
+  v = warp_reduce(v, op);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect red reuse
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = (l < (blockDim.x >> 5)) ? red[l] : identity;
+  r = warp_reduce(r, op);
+  return r;
+}
+
+__device__ __forceinline__ void load_row_to_smem(__half* dst, const __half* src, int H) {
+  // H % 8 == 0 guaranteed by the host wrapper
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) d[i] = __ldg(s + i);
+}
+
+__device__ __forceinline__ void store_q8(int8_t* dst, int i8, const float (&v)[8], float scale) {
+  // 8 int8 values = one 64-bit store
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lo |= (static_cast<uint32_t>(static_cast<uint8_t>(cvt_s8(__fmul_rn(v[j], scale)))) << (8 * j));
+    hi |= (static_cast<uint32_t>(static_cast<uint8_t>(cvt_s8(__fmul_rn(v[4 + j], scale)))) << (8 * j));
+  }
+  reinterpret_cast<uint2*>(dst)[i8] = make_uint2(lo, hi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// N1: rms_norm_general[_fuse_sum]  (generalLayerNorm[_fuse_sum], layernorm_kernels.cu:53-326)
+//     mean-subtracting layer norm + per-token INT8 quant (+ fp16-accumulated row sum, reference thread grouping)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) layernorm_quant_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
+                                                                  const __half* __restrict__ gamma, __half* __restrict__ input_sum,
+                                                                  __half* __restrict__ scaling, float eps, int H, int ref_block,
+                                                                  bool per_token) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __half* sx = reinterpret_cast<__half*>(sm);  // x row
+  __half* sy = sx + H;                         // half(y) row (only for the fused sum)
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
+  __syncthreads();
+
+  float s = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      s += f.x + f.y;
+    }
+  }
+  const float mean = __fdiv_rn(block_reduce(s, red, OpSum(), 0.f), static_cast<float>(H));
+  float vs = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      const float a = f.x - mean, b = f.y - mean;
+      vs += a * a + b * b;
+    }
+  }
+  const float var = block_reduce(vs, red, OpSum(), 0.f);
+  const float rstd = __frsqrt_rn(__fadd_rn(__fdiv_rn(var, static_cast<float>(H)), eps));
+
+  if (!per_token) {
+    // per-tensor static scale: q = rni_sat(half(y) * scale)   (layernorm_kernels.cu:159-163)
+    const float sc = __half2float(scaling[0]);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+      const float y = __fmul_rn(__fmul_rn(__fsub_rn(__half2float(sx[i]), mean), rstd), __half2float(gamma[i]));
+      out[static_cast<size_t>(row) * H + i] = cvt_s8(__fmul_rn(__half2float(__float2half_rn(y)), sc));
+    }
+    return;
+  }
+
+  // pass 3: amax of half(y) (init 1e-6 in fp16), optionally stash half(y) for the sum
+  float amax = __half2float(__float2half_rn(1e-6f));
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    const __half* gh = reinterpret_cast<const __half*>(&g);
+    uint4 yv;
+    __half* yh = reinterpret_cast<__half*>(&yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = __fmul_rn(__fmul_rn(__fsub_rn(__half2float(h[j]), mean), rstd), __half2float(gh[j]));
+      yh[j] = __float2half_rn(y);
+      amax = fmaxf(amax, fabsf(__half2float(yh[j])));
+    }
+    if (input_sum) reinterpret_cast<uint4*>(sy)[i] = yv;
+  }
+  amax = block_reduce(amax, red, OpMax(), 0.f);  // (includes the barrier that publishes sy)
+  if (input_sum) {
+    // reference thread t (of ref_block threads) accumulates y_h[t], y_h[t+B], ... sequentially IN FP16 (:275,286)
+    float part = 0.f;
+    for (int t = threadIdx.x; t < ref_block; t += blockDim.x) {
+      __half acc = __float2half_rn(0.f);
+      for (int i = t; i < H; i += ref_block) acc = __hadd(acc, sy[i]);
+      part += __half2float(acc);
+    }
+    const float total = block_reduce(part, red, OpSum(), 0.f);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+  }
+  if (threadIdx.x == 0) scaling[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+  const float qs_ = __fdiv_rn(127.f, amax);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    const __half* gh = reinterpret_cast<const __half*>(&g);
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = __fmul_rn(__fmul_rn(__fsub_rn(__half2float(h[j]), mean), rstd), __half2float(gh[j]));
+    store_q8(out + static_cast<size_t>(row) * H, i, y, qs_);  // quantises the UN-rounded fp32 y (:307-318)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q1: invoke_quant / invoke_quant_fuse_sum (per-token)   fused_kernels.cu:52-137
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) quant_per_token_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
+                                                                  __half* __restrict__ input_sum, __half* __restrict__ scale, int H) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __half* sx = reinterpret_cast<__half*>(sm);
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
+  __syncthreads();
+  float amax = 0.f, s = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      s += f.x + f.y;
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  amax = block_reduce(amax, red, OpMax(), 0.f);
+  if (input_sum) {
+    const float total = block_reduce(s, red, OpSum(), 0.f);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+  }
+  if (threadIdx.x == 0) scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+  const float qs_ = __fdiv_rn(127.f, amax);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __half2float(h[j]);
+    store_q8(out + static_cast<size_t>(row) * H, i, x, qs_);
+  }
+}
+
+__global__ void quant_scalar_kernel(int8_t* __restrict__ out, const __half* __restrict__ in, float scale, size_t n) {
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = cvt_s8(__fdiv_rn(__half2float(in[i]), scale));
+}
+
+// ------------------------------------------------------------------------------------------------
+// N2: rms_norm   layernorm_kernels.cu:330-360
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) rms_norm_kernel(void* __restrict__ out, const __half* __restrict__ in,
+                                                           const __half* __restrict__ weight, float eps, int H, bool use_quant) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __half* sx = reinterpret_cast<__half*>(sm);
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
+  __syncthreads();
+  float vs = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      vs += f.x * f.x + f.y * f.y;
+    }
+  }
+  const float var = block_reduce(vs, red, OpSum(), 0.f);
+  const float rstd = __frsqrt_rn(__fadd_rn(__fdiv_rn(var, static_cast<float>(H)), eps));
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(weight) + i);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    const __half* gh = reinterpret_cast<const __half*>(&g);
+    if (use_quant) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = __fmul_rn(__fmul_rn(__half2float(h[j]), rstd), __half2float(gh[j]));
+      store_q8(static_cast<int8_t*>(out) + static_cast<size_t>(row) * H, i, y, 1.0f);
+    } else {
+      uint4 o;
+      __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) oh[j] = __hmul(__float2half_rn(__fmul_rn(__half2float(h[j]), rstd)), gh[j]);  // fp16 product (:356-357)
+      reinterpret_cast<uint4*>(static_cast<__half*>(out) + static_cast<size_t>(row) * H)[i] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A0: silu_and_mul   activation_kernels.cu:10-30
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ __half silu_h(__half x) {
+  const float f = __half2float(x);
+  return __float2half_rn(__fdiv_rn(f, __fadd_rn(1.0f, expf(-f))));
+}
+
+__global__ void __launch_bounds__(kThreads) silu_and_mul_kernel(__half* __restrict__ out, const __half* __restrict__ in, int d) {
+  const int row = blockIdx.x;
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d);
+  const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d);
+  uint4* go = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * d);
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < d / 8; i += gridDim.y * blockDim.x) {
+    const uint4 x = __ldg(gx + i), y = __ldg(gy + i);
+    const __half* xh = reinterpret_cast<const __half*>(&x);
+    const __half* yh = reinterpret_cast<const __half*>(&y);
+    uint4 o;
+    __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) oh[j] = __hmul(silu_h(xh[j]), yh[j]);
+    go[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// legacy exports (not reached by llama_w4a8 / llama_w8a8; API completeness)
+// ------------------------------------------------------------------------------------------------
+__global__ void gelu_kernel(__half* __restrict__ out, const __half* __restrict__ in, size_t n, bool fast) {
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const __half x = in[i];
+    __half t;
+    if (!fast) {  // activation_kernels.cu:166-170, every T expression rounded to fp16
+      const float x3 = __half2float(__hmul(__hmul(x, x), x));
+      const __half inner = __float2half_rn(__fmul_rn(0.044715f, x3));
+      const __half arg = __float2half_rn(__fmul_rn(0.79788456f, __half2float(__hadd(x, inner))));
+      t = __float2half_rn(tanhf(__half2float(arg)));
+    } else {  // :172-178
+      const float f = __half2float(x);
+      const __half a = __float2half_rn(__fmul_rn(f, 0.79788456f));
+      const __half b = __hadd(__float2half_rn(1.0f), __hmul(__float2half_rn(__fmul_rn(0.044715f, f)), x));
+      t = __float2half_rn(tanhf(__half2float(__hmul(a, b))));
+    }
+    out[i] = __hmul(__hmul(__float2half_rn(0.5f), x), __hadd(__float2half_rn(1.0f), t));
+  }
+}
+
+__global__ void dequant_add_residual_kernel(__half* __restrict__ out, const int32_t* __restrict__ in, const __half* __restrict__ residual,
+                                            const __half* __restrict__ scale_vec, float scale, int H) {
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const int row = blockIdx.x;
+  const float sc = scale_vec ? __half2float(scale_vec[row]) : scale;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const size_t o = static_cast<size_t>(row) * H + i;
+    out[o] = __float2half_rn(__fadd_rn(__fmul_rn(__int2float_rn(in[o]), sc), __half2float(residual[o])));
+  }
+}
+
+__global__ void dequant_kernel(__half* __restrict__ out, const int32_t* __restrict__ in, float scale, int H, int in_stride, int out_stride) {
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const int row = blockIdx.x;
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    out[static_cast<size_t>(row) * out_stride + i] = __float2half_rn(__fmul_rn(__int2float_rn(in[static_cast<size_t>(row) * in_stride + i]), scale));
+}
+
+__global__ void __launch_bounds__(kThreads) dequant_add_residual_rms_norm_quant_kernel(int8_t* __restrict__ out, const int32_t* __restrict__ in,
+                                                                                      __half* __restrict__ residual, const __half* __restrict__ gamma,
+                                                                                      const __half* __restrict__ scale_vec, float scale, float eps, int H) {
+  __shared__ float red[32];
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const int row = blockIdx.x;
+  const float sc = scale_vec ? __half2float(scale_vec[row]) : scale;
+  float vs = 0.f;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const size_t o = static_cast<size_t>(row) * H + i;
+    const float d = __fadd_rn(__fmul_rn(__int2float_rn(in[o]), sc), __half2float(residual[o]));
+    residual[o] = __float2half_rn(d);
+    vs += d * d;
+  }
+  const float var = block_reduce(vs, red, OpSum(), 0.f);
+  const float rstd = __frsqrt_rn(__fadd_rn(__fdiv_rn(var, static_cast<float>(H)), eps));
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const size_t o = static_cast<size_t>(row) * H + i;
+    out[o] = cvt_s8(__fmul_rn(__fmul_rn(__half2float(residual[o]), rstd), __half2float(gamma[i])));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) dequant_silu_and_mul_quant_kernel(int8_t* __restrict__ out, const int32_t* __restrict__ in, int d,
+                                                                             float scale_gate, float scale_up, float scale_out,
+                                                                             float* __restrict__ scale_out_vec, float* __restrict__ tmp) {
+  __shared__ float red[32];
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const int row = blockIdx.x;
+  const int32_t* g = in + static_cast<size_t>(row) * 2 * d;
+  if (scale_out_vec == nullptr) {
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      const float x = __fmul_rn(__int2float_rn(g[i]), scale_gate), y = __fmul_rn(__int2float_rn(g[d + i]), scale_up);
+      const float s = __fdiv_rn(x, __fadd_rn(1.0f, expf(-x)));
+      out[static_cast<size_t>(row) * d + i] = cvt_s8(__fdiv_rn(__fmul_rn(s, y), scale_out));
+    }
+    return;
+  }
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    const float x = __fmul_rn(__int2float_rn(g[i]), scale_gate), y = __fmul_rn(__int2float_rn(g[d + i]), scale_up);
+    const float t = __fmul_rn(__fdiv_rn(x, __fadd_rn(1.0f, expf(-x))), y);
+    tmp[static_cast<size_t>(row) * d + i] = t;
+    amax = fmaxf(amax, fabsf(t));
+  }
+  amax = block_reduce(amax, red, OpMax(), 0.f);
+  if (threadIdx.x == 0) scale_out_vec[row] = __fdiv_rn(amax, 127.f);
+  const float qs_ = __fdiv_rn(127.f, amax);
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    out[static_cast<size_t>(row) * d + i] = cvt_s8(__fmul_rn(qs_, tmp[static_cast<size_t>(row) * d + i]));
+}
+
+template <typename Kern, typename... Args>
+int launch(Kern kern, dim3 grid, dim3 block, size_t smem, void* stream, const char* what, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, args...), what);
+}
+
+template <typename Kern>
+int ensure_smem(Kern kern, size_t bytes, const char* what) {
+  if (bytes <= 48 * 1024) return QS_OK;
+  QS_REQUIRE(bytes <= 200 * 1024, "%s: row of %zu bytes does not fit in shared memory", what, bytes);
+  return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), what);
+}
+
+}  // namespace
+
+int rms_norm(void* out, const void* in, const void* weight, float eps, int use_quant, int tokens, int hidden, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "rms_norm: hidden=%d must be a positive multiple of 8", hidden);
+  const size_t smem = static_cast<size_t>(hidden) * 2;
+  int rc = ensure_smem(rms_norm_kernel, smem, "rms_norm");
+  if (rc) return rc;
+  return launch(rms_norm_kernel, dim3(tokens), dim3(kThreads), smem, stream, "rms_norm", out, static_cast<const __half*>(in),
+                static_cast<const __half*>(weight), eps, hidden, use_quant != 0);
+}
+
+int layernorm_general_quant(void* out_q, const void* in, const void* gamma, void* input_sum, void* scaling, float eps, int tokens, int hidden,
+                            int per_token, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "rms_norm_general: hidden=%d must be a positive multiple of 8", hidden);
+  QS_REQUIRE(per_token || input_sum == nullptr, "rms_norm_general_fuse_sum: per-tensor scaling with input_sum is not implemented by the reference either (layernorm_kernels.cu:490-494)");
+  const size_t smem = static_cast<size_t>(hidden) * 2 * (input_sum ? 2 : 1);
+  int rc = ensure_smem(layernorm_quant_kernel, smem, "rms_norm_general");
+  if (rc) return rc;
+  int ref_block = hidden < 1024 ? hidden : 1024;
+  ref_block = 32 * ((ref_block + 31) / 32);  // layernorm_kernels.cu:433-436
+  return launch(layernorm_quant_kernel, dim3(tokens), dim3(kThreads), smem, stream, "rms_norm_general", static_cast<int8_t*>(out_q),
+                static_cast<const __half*>(in), static_cast<const __half*>(gamma), static_cast<__half*>(input_sum),
+                static_cast<__half*>(scaling), eps, hidden, ref_block, per_token != 0);
+}
+
+int quant_per_token(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int hidden, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "invoke_quant: hidden=%d must be a positive multiple of 8", hidden);
+  const size_t smem = static_cast<size_t>(hidden) * 2;
+  int rc = ensure_smem(quant_per_token_kernel, smem, "invoke_quant");
+  if (rc) return rc;
+  return launch(quant_per_token_kernel, dim3(tokens), dim3(kThreads), smem, stream, "invoke_quant", static_cast<int8_t*>(out_q),
+                static_cast<const __half*>(in), static_cast<__half*>(input_sum), static_cast<__half*>(scale), hidden);
+}
+
+int quant_scalar(void* out_q, const void* in, float scale, int tokens, int hidden, void* stream) {
+  const size_t n = static_cast<size_t>(tokens) * hidden;
+  if (n == 0) return QS_OK;
+  const int grid = static_cast<int>((n + 1023) / 1024 < 2048 ? (n + 1023) / 1024 : 2048);
+  return launch(quant_scalar_kernel, dim3(grid), dim3(256), 0, stream, "invoke_quant(scalar)", static_cast<int8_t*>(out_q),
+                static_cast<const __half*>(in), scale, n);
+}
+
+int silu_and_mul(void* out, const void* in, int tokens, int d, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(d > 0 && d % 8 == 0, "silu_and_mul: d=%d must be a positive multiple of 8", d);
+  const int bx = (d / 8 + kThreads - 1) / kThreads;
+  return launch(silu_and_mul_kernel, dim3(tokens, bx), dim3(kThreads), 0, stream, "silu_and_mul", static_cast<__half*>(out),
+                static_cast<const __half*>(in), d);
+}
+
+int gelu(void* out, const void* in, int tokens, int d, int fast, void* stream) {
+  const size_t n = static_cast<size_t>(tokens) * d;
+  if (n == 0) return QS_OK;
+  const int grid = static_cast<int>((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  return launch(gelu_kernel, dim3(grid), dim3(256), 0, stream, "gelu", static_cast<__half*>(out), static_cast<const __half*>(in), n, fast != 0);
+}
+
+int dequant_add_residual(void* out, const void* in_i32, const void* residual, const void* scale_vec, float scale, int tokens, int hidden,
+                         void* stream) {
+  if (tokens == 0) return QS_OK;
+  return launch(dequant_add_residual_kernel, dim3(tokens), dim3(kThreads), 0, stream, "invoke_dequant_add_residual", static_cast<__half*>(out),
+                static_cast<const int32_t*>(in_i32), static_cast<const __half*>(residual), static_cast<const __half*>(scale_vec), scale, hidden);
+}
+
+int dequant(void* out, const void* in_i32, float scale, int tokens, int hidden, int in_stride, int out_stride, void* stream) {
+  if (tokens == 0) return QS_OK;
+  return launch(dequant_kernel, dim3(tokens), dim3(kThreads), 0, stream, "invoke_dequant", static_cast<__half*>(out),
+                static_cast<const int32_t*>(in_i32), scale, hidden, in_stride, out_stride);
+}
+
+int dequant_add_residual_rms_norm_quant(void* out_q, const void* in_i32, void* residual, const void* gamma, const void* scale_vec, float scale,
+                                        float eps, int tokens, int hidden, void* stream) {
+  if (tokens == 0) return QS_OK;
+  return launch(dequant_add_residual_rms_norm_quant_kernel, dim3(tokens), dim3(kThreads), 0, stream, "invoke_dequant_add_residual_rms_norm_quant",
+                static_cast<int8_t*>(out_q), static_cast<const int32_t*>(in_i32), static_cast<__half*>(residual),
+                static_cast<const __half*>(gamma), static_cast<const __half*>(scale_vec), scale, eps, hidden);
+}
+
+int dequant_silu_and_mul_quant(void* out_q, const void* in_i32, float scale_gate, float scale_up, float scale_out, void* scale_out_vec, void* tmp,
+                               int tokens, int d, void* stream) {
+  if (tokens == 0) return QS_OK;
+  return launch(dequant_silu_and_mul_quant_kernel, dim3(tokens), dim3(kThreads), 0, stream, "invoke_dequant_silu_and_mul_quant",
+                static_cast<int8_t*>(out_q), static_cast<const int32_t*>(in_i32), d, scale_gate, scale_up, scale_out,
+                static_cast<float*>(scale_out_vec), static_cast<float*>(tmp));
+}
+
+int silu_and_mul_quant(void*, const void*, void*, void*, int, int, void*) {
+  return set_error(QS_ERR_UNSUPPORTED, "silu_and_mul_quant: not built in this revision");
+}
+
+}  // namespace qs

@@ -1,0 +1,85 @@
+// qserve_b200 -- internal host-side launch interfaces shared by the translation units.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace qs {
+
+bool pdl_enabled();
+
+struct GemmArgs {
+  const void* act = nullptr;        // int8 [M, K]
+  const void* weight = nullptr;     // W4: packed int4 [N, K/2] (reference layout); W8: int8 [N, K]
+  const void* s2_scales = nullptr;  // per-group
+  const void* s2_zeros = nullptr;   // per-group
+  const void* wscales = nullptr;    // fp16 [N]
+  const void* w_szs = nullptr;      // fp16 [N] per-channel
+  const void* ascales = nullptr;    // fp16 [M]
+  const void* a_ssums = nullptr;    // fp16 [M] per-channel
+  void* out = nullptr;              // fp16 [M, N]
+  void* acc_out = nullptr;          // optional int32 [M, N]
+  int M = 0, N = 0, K = 0;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  int force_units_per_cta = 0;  // tests: force a stream-K decomposition
+  void* stream = nullptr;
+};
+
+int gemm_w4a8_per_chn(const GemmArgs& a);
+int gemm_w4a8_per_group(const GemmArgs& a);
+int gemm_w8a8(const GemmArgs& a);
+size_t gemm_workspace_bytes();
+
+// elementwise.cu
+int rms_norm(void* out, const void* in, const void* weight, float eps, int use_quant, int tokens, int hidden, void* stream);
+int layernorm_general_quant(void* out_q, const void* in, const void* gamma, void* input_sum, void* scaling, float eps, int tokens,
+                            int hidden, int per_token, void* stream);
+int quant_per_token(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int hidden, void* stream);
+int quant_scalar(void* out_q, const void* in, float scale, int tokens, int hidden, void* stream);
+int silu_and_mul(void* out, const void* in, int tokens, int d, void* stream);
+int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int d, void* stream);
+int gelu(void* out, const void* in, int tokens, int d, int fast, void* stream);
+int dequant_add_residual(void* out, const void* in_i32, const void* residual, const void* scale_vec, float scale, int tokens, int hidden,
+                         void* stream);
+int dequant(void* out, const void* in_i32, float scale, int tokens, int hidden, int in_stride, int out_stride, void* stream);
+int dequant_add_residual_rms_norm_quant(void* out_q, const void* in_i32, void* residual, const void* gamma, const void* scale_vec,
+                                        float scale, float eps, int tokens, int hidden, void* stream);
+int dequant_silu_and_mul_quant(void* out_q, const void* in_i32, float scale_gate, float scale_up, float scale_out, void* scale_out_vec,
+                               void* tmp, int tokens, int d, void* stream);
+
+// attention.cu
+struct DecodeAttnArgs {
+  const void* q = nullptr;  // fp16, row stride q_stride elements
+  const void* k = nullptr;
+  const void* v = nullptr;
+  long long q_stride = 0, k_stride = 0, v_stride = 0;
+  const long long* kv_pointers = nullptr;  // [B, 2, max_blocks] absolute device addresses
+  const int* lengths = nullptr;            // [B] context length including the new token
+  void* out = nullptr;                     // fp16 [B, Hq, D] contiguous
+  int batch = 0, num_heads = 0, num_kv_heads = 0, head_dim = 0, max_blocks = 0;
+  int tokens_per_block = 64, size_per_token = 0, timestep = 0, memory_max_len = 0;
+  int rotary_dim = 0;
+  float rotary_base = 10000.f;
+  int int4_kv = 1, kv_zeros = 1;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  void* stream = nullptr;
+};
+int decode_attention(const DecodeAttnArgs& a);
+size_t attention_workspace_bytes(int batch, int num_heads, int head_dim, int max_splits);
+
+struct PrefillAppendArgs {
+  void* qkv = nullptr;  // fp16 [T, (Hq + 2 Hkv) * D], q and k rotated in place
+  const int* seq_lens = nullptr;
+  const int* padding_offset = nullptr;
+  const long long* kv_pointers = nullptr;  // may be null: rotate only
+  int batch = 0, num_tokens = 0, max_blocks = 0, num_heads = 0, num_kv_heads = 0, head_dim = 0;
+  int seq_len = 0, tokens_per_block = 64, size_per_token = 0, rotary_dim = 0, max_positions = 0;
+  float rotary_base = 10000.f;
+  int int4_kv = 1, kv_zeros = 1;
+  void* stream = nullptr;
+};
+int prefill_rope_append(const PrefillAppendArgs& a);
+int padding_offsets(int* out, const int* cu_seqlens, int batch, int max_seqlen, void* stream);
+
+}  // namespace qs
