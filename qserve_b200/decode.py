@@ -1,0 +1,253 @@
+"""Decode-step runner: the reference's per-layer op sequence over the drop-in `qserve_backend` API, with persistent
+activation buffers and whole-step CUDA-graph capture.
+
+This is the measurement harness for BASELINE.json's metric (tokens/s, Llama-3-8B W4A8KV4 decode) and the
+"step-level CUDA-graph runner under the unchanged model code" of SURVEY.md section 8f-2.  It issues exactly the calls
+`LlamaDecoderLayer.forward` issues (qserve/modeling/models/llama_w4a8_unpad.py:330-361, 69-93, 186-291; W8A8:
+llama_w8a8_unpad.py) with the same argument marshalling, on synthetic weights of the named architecture
+(random INT4/INT8 codes, scales chosen so that activations stay O(1); there is no network for checkpoints).
+
+Tensor parallelism is Megatron style: qkv / gate_up column parallel, o_proj / down_proj row parallel
+(split along K in multiples of 128), KV heads sharded, one NCCL sum-allreduce of [M, hidden] fp16 after each row-parallel
+GEMM.  Every rank quantises its own activation shard with its own per-token scale, so each rank's partial product is a
+correctly de-quantised partial sum (results agree with the single-GPU run to quantisation noise, not bit-for-bit).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+import qserve_backend.activation_ops as activation_ops
+import qserve_backend.fused_attention as fused_attention
+import qserve_backend.fused_kernels as fused_kernels
+import qserve_backend.layernorm_ops as layernorm_ops
+import qserve_backend.qgemm_w4a8_per_chn as qgemm_chn
+import qserve_backend.qgemm_w4a8_per_group as qgemm_grp
+import qserve_backend.qgemm_w8a8 as qgemm_w8
+
+
+@dataclass(frozen=True)
+class ModelConfig:
+    name: str
+    hidden: int
+    intermediate: int
+    heads: int
+    kv_heads: int
+    layers: int
+    vocab: int
+    rope_theta: float
+    eps: float = 1e-5
+    head_dim: int = 128
+    max_pos: int = 8192
+
+
+MODELS = {
+    "llama-3-8b": ModelConfig("Llama-3-8B", 4096, 14336, 32, 8, 32, 128256, 500000.0),
+    "mistral-7b": ModelConfig("Mistral-7B", 4096, 14336, 32, 8, 32, 32000, 10000.0, max_pos=32768),
+    "llama-2-7b": ModelConfig("Llama-2-7B", 4096, 11008, 32, 32, 32, 32000, 10000.0, max_pos=4096),
+    "qwen1.5-72b": ModelConfig("Qwen1.5-72B", 8192, 24576, 64, 64, 80, 152064, 1000000.0, eps=1e-6, max_pos=32768),
+    "tiny": ModelConfig("tiny-test", 512, 1024, 4, 2, 2, 1024, 10000.0),
+}
+
+PRECISIONS = ("w4a8kv4", "w4a8kv4-g128", "w8a8kv8", "w4a8kv8", "w8a8kv4")
+
+
+class _Linear:
+    """Weights of one quantised linear layer in the reference's buffer layout (w4a8_linear.py:38-103, w8a8_linear.py:45-54)."""
+
+    def __init__(self, N: int, K: int, mode: str, dev, gen):
+        self.N, self.K, self.mode = N, K, mode
+        r = lambda lo, hi, shape, dt: torch.randint(lo, hi, shape, dtype=dt, device=dev, generator=gen)
+        u = lambda lo, hi, shape: (torch.rand(shape, device=dev, generator=gen) * (hi - lo) + lo)
+        target = 1.0 / (K ** 0.5)  # output std ~ O(1) for unit-variance inputs
+        if mode == "w8":
+            self.weight = r(-127, 128, (N, K), torch.int8)
+            self.wscale = (u(0.8, 1.2, (N,)) * target / 73.0).half()
+        else:
+            self.qweight = r(-128, 128, (N, K // 2), torch.int8)  # uniform random nibbles
+            if mode == "chn":
+                self.s1 = (u(0.8, 1.2, (N,)) * target / 4.6).half()
+                z = r(7, 9, (N,), torch.int8).float()
+                self.s1z = (z * self.s1.float()).half()
+            else:
+                g = K // 128
+                s2 = r(1, 9, (g, N), torch.int8)
+                z = r(7, 9, (g, N), torch.int8)
+                self.s2_scales = s2.contiguous()
+                self.s2_zeros = (-(z.int()) * s2.int()).to(torch.int8).contiguous()
+                self.s1 = (u(0.8, 1.2, (N,)) * target / (4.6 * 4.5)).half()
+
+    def __call__(self, x_q, scale, asum, out):
+        if self.mode == "chn":    # w4a8_linear.py:106-115
+            qgemm_chn.gemm_forward_cuda(x_q, self.qweight, self.s1, scale, self.s1z, asum, out)
+        elif self.mode == "grp":  # w4a8_linear.py:121-131
+            qgemm_grp.gemm_forward_cuda(x_q, self.qweight, self.s2_zeros, self.s2_scales, self.s1, scale, out)
+        else:                     # w8a8_linear.py:98-101
+            qgemm_w8.w8a8_gemm_forward_cuda(x_q, self.weight, self.wscale, scale, out)
+
+    def weight_bytes(self) -> int:
+        return self.N * self.K if self.mode == "w8" else self.N * self.K // 2
+
+
+class DecodeRunner:
+    def __init__(self, model: str = "llama-3-8b", precision: str = "w4a8kv4", batch: int = 64, ctx: int = 1024,
+                 device: Optional[torch.device] = None, tp_rank: int = 0, tp_size: int = 1, seed: int = 0, layers: Optional[int] = None,
+                 process_group=None):
+        assert precision in PRECISIONS, precision
+        self.cfg = cfg = MODELS[model]
+        self.precision, self.batch, self.ctx = precision, batch, ctx
+        self.dev = dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.tp_rank, self.tp_size, self.pg = tp_rank, tp_size, process_group
+        self.L = layers if layers is not None else cfg.layers
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed + 1000 * tp_rank)
+        self.wmode = "w8" if precision.startswith("w8a8") else ("grp" if precision.endswith("g128") else "chn")
+        self.act_sum = self.wmode == "chn"  # per-channel W4 needs the activation sum (llama_w4a8_unpad.py:69, 165-168)
+        self.kv_bits = 4 if "kv4" in precision else 8
+        D, H, I = cfg.head_dim, cfg.hidden, cfg.intermediate
+        assert cfg.heads % tp_size == 0 and I % (128 * tp_size) == 0
+        self.Hq = cfg.heads // tp_size
+        self.Hkv = max(1, cfg.kv_heads // tp_size)  # llama_w4a8_unpad.py:120-129
+        self.Iloc = I // tp_size
+        self.q_size, self.kv_size = self.Hq * D, self.Hkv * D
+        M = batch
+
+        # ---- weights --------------------------------------------------------------------------------------
+        self.layers = []
+        for _ in range(self.L):
+            self.layers.append({
+                "qkv": _Linear(self.q_size + 2 * self.kv_size, H, self.wmode, dev, gen),
+                "o": _Linear(H, self.q_size, self.wmode, dev, gen),
+                "gate_up": _Linear(2 * self.Iloc, H, self.wmode, dev, gen),
+                "down": _Linear(H, self.Iloc, self.wmode, dev, gen),
+                # W4A8 checkpoints skip the norm weights (gamma = 1, llama_w4a8_unpad.py:541-542); W8A8 loads them
+                "ln1": torch.ones(H, dtype=torch.half, device=dev),
+                "ln2": torch.ones(H, dtype=torch.half, device=dev),
+            })
+        self.norm_w = torch.ones(H, dtype=torch.half, device=dev)
+        self.embed = (torch.randn((cfg.vocab, H), device=dev, generator=gen) * 1.0).half()
+        self.lm_head = (torch.randn((cfg.vocab, H), device=dev, generator=gen) * (1.0 / H ** 0.5)).half()  # fp16, cuBLAS (:432)
+
+        # ---- paged KV cache: ctx tokens present, the step decodes token ctx (length ctx+1) ---------------------
+        self.blocks_per_seq = (ctx + 1 + 63) // 64
+        self.size_per_token = self.Hkv * D * self.kv_bits // 8
+        code_bytes = 64 * self.size_per_token
+        self.page_bytes = code_bytes + self.Hkv * 64 * 4  # cache_engine.py:62-66
+        n_pages = batch * self.blocks_per_seq
+        self.kpools, self.vpools, tables = [], [], []
+        blk = torch.arange(n_pages, device=dev, dtype=torch.int64).view(batch, self.blocks_per_seq)
+        for _ in range(self.L):
+            pools = []
+            for _kv in range(2):
+                pool = torch.randint(0, 256, (n_pages, self.page_bytes), dtype=torch.uint8, device=dev, generator=gen)
+                meta = pool[:, code_bytes:].view(torch.float16).view(n_pages, 2, self.Hkv, 64)
+                meta[:, 0] = (torch.rand((n_pages, self.Hkv, 64), device=dev, generator=gen) * 0.09 + 0.01).half()
+                zmax = 15.0 if self.kv_bits == 4 else 255.0
+                meta[:, 1] = (torch.rand((n_pages, self.Hkv, 64), device=dev, generator=gen) * zmax).half()
+                pools.append(pool)
+            self.kpools.append(pools[0]); self.vpools.append(pools[1])
+            # [B, 2, blocks] absolute addresses (model_runner.py:506-530)
+            tables.append(torch.stack([pools[0].data_ptr() + blk * self.page_bytes, pools[1].data_ptr() + blk * self.page_bytes], dim=1))
+        self.block_tables = torch.stack(tables, dim=0).contiguous()  # [L, B, 2, blocks]
+        self.context_lens = torch.full((batch,), ctx + 1, dtype=torch.int32, device=dev)
+        self.max_seq_len = ctx + 1
+
+        # ---- persistent ActivationBuffer (input_metadata.py:71-109; aliasing kept) ------------------------------
+        self.act_buffer = torch.empty(M * max(self.q_size + 2 * self.kv_size, 2 * self.Iloc), dtype=torch.half, device=dev)
+        self.qkv_buf = self.act_buffer[: M * (self.q_size + 2 * self.kv_size)].view(M, -1)
+        self.out_buf = self.act_buffer[: M * H].view(M, H)
+        self.gate_up_buf = self.act_buffer[: M * 2 * self.Iloc].view(M, -1)
+        self.q_act = torch.empty(M * max(H, self.Iloc), dtype=torch.int8, device=dev)
+        self.q_hidden = self.q_act[: M * H].view(M, H)
+        self.q_attn = self.q_act[: M * self.q_size].view(M, self.q_size)
+        self.q_mlp = self.q_act[: M * self.Iloc].view(M, self.Iloc)
+        self.q_scale = torch.empty(M, dtype=torch.half, device=dev)
+        self.q_sum = torch.empty(M, dtype=torch.half, device=dev)
+        self.mlp_act = torch.empty((M, self.Iloc), dtype=torch.half, device=dev)  # reference: fresh torch.empty per call (activation.py:26)
+        self.tokens_in = torch.zeros(M, dtype=torch.int64, device=dev)
+        self.tokens_out = torch.zeros(M, dtype=torch.int64, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _norm_quant(self, x, gamma):
+        if self.act_sum:  # layernorm.py:88
+            layernorm_ops.rms_norm_general_fuse_sum(self.q_hidden, x, gamma, self.q_sum, self.q_scale, self.cfg.eps, True)
+        else:             # layernorm.py:72
+            layernorm_ops.rms_norm_general(self.q_hidden, x, gamma, self.q_scale, self.cfg.eps, True)
+
+    def _quant(self, out_q, x):
+        if self.act_sum:  # llama_w4a8_unpad.py:177-183
+            fused_kernels.invoke_quant_fuse_sum(out_q, x, self.q_sum, self.q_scale)
+        else:
+            fused_kernels.invoke_quant(out_q, x, self.q_scale)
+
+    def _allreduce(self, t):
+        if self.tp_size > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+
+    def forward(self, tokens: torch.Tensor) -> torch.Tensor:
+        """One decode step for `batch` sequences; returns the greedy next tokens [batch] (device)."""
+        cfg, D = self.cfg, self.cfg.head_dim
+        n = 0
+        hidden = self.embed[tokens]  # LlamaModel.forward (:401-404)
+        for li, ly in enumerate(self.layers):
+            residual = hidden
+            self._norm_quant(hidden, ly["ln1"])
+            ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
+            q, k, v = self.qkv_buf.split([self.q_size, self.kv_size, self.kv_size], dim=-1)  # :245-252
+            q = q.reshape(q.size(0), self.Hq, D)
+            k = k.reshape(k.size(0), self.Hkv, D)
+            v = v.reshape(v.size(0), self.Hkv, D)
+            attn = fused_attention.single_query_attention(
+                q, k, v, self.block_tables[li], self.context_lens, None, min(8192, cfg.max_pos), 64, self.size_per_token,
+                self.max_seq_len, D, cfg.rope_theta, True, self.kv_bits == 4, True)  # :265-281
+            attn = attn.reshape(q.size(0), -1)
+            self._quant(self.q_attn, attn)
+            ly["o"](self.q_attn, self.q_scale, self.q_sum, self.out_buf)
+            self._allreduce(self.out_buf)
+            hidden = residual + self.out_buf  # :348
+            residual = hidden
+            self._norm_quant(hidden, ly["ln2"])
+            ly["gate_up"](self.q_hidden, self.q_scale, self.q_sum, self.gate_up_buf)
+            activation_ops.silu_and_mul(self.mlp_act, self.gate_up_buf)  # activation.py:24-29
+            self._quant(self.q_mlp, self.mlp_act)
+            ly["down"](self.q_mlp, self.q_scale, self.q_sum, self.out_buf)
+            self._allreduce(self.out_buf)
+            hidden = residual + self.out_buf  # :360
+            n += 10
+        out = torch.empty_like(hidden)
+        layernorm_ops.rms_norm(out, hidden, self.norm_w, cfg.eps, False)  # final norm (:408)
+        logits = torch.nn.functional.linear(out, self.lm_head)           # fp16 lm_head (:474-476)
+        self.launches_per_step = n + 1
+        return torch.argmax(logits, dim=-1)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def capture(self, warmup: int = 2) -> None:
+        """Warm up eagerly (allocates workspaces, sets kernel attributes) and capture the whole step in a CUDA graph."""
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):
+                self.tokens_out.copy_(self.forward(self.tokens_in))
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(g):
+            self.tokens_out.copy_(self.forward(self.tokens_in))
+        self.graph = g
+
+    def step(self) -> None:
+        """Replay the captured step: tokens_in -> tokens_out (both device resident)."""
+        self.graph.replay()
+
+    def weight_bytes_per_step(self) -> int:
+        return sum(l.weight_bytes() for ly in self.layers for l in (ly["qkv"], ly["o"], ly["gate_up"], ly["down"]))
+
+    def kv_bytes_per_step(self) -> int:
+        """Algorithmic KV traffic: codes + scale/zero of K and V for ctx tokens, + q in / o out."""
+        B, D = self.batch, self.cfg.head_dim
+        per_layer = B * self.Hkv * self.ctx * D * self.kv_bits // 8 * 2 + B * self.Hkv * self.ctx * 8 + 4 * B * self.Hq * D
+        return per_layer * self.L

@@ -7,7 +7,8 @@ Stated tolerances
     reduction feeding the codes) the INT8 output and the scale are required to be bit-exact.
   * fp16 scales: bit-exact for invoke_quant, <= 1 fp16 ulp for the norm (amax of half(y)).
   * fp16 row sums: <= 2 fp16 ulp or 2e-3 absolute (order-dependent fp32 sum, then fp16 rounding).
-  * silu_and_mul: <= 1 fp16 ulp (expf implementations differ in the last fp32 bit).
+  * silu_and_mul: <= 2 fp16 ulp, < 0.1% of the elements differ at all (expf implementations differ in the last fp32 bit;
+    a 1-ulp difference of half(silu) can become 2 ulp after the fp16 product).
 """
 import numpy as np
 import pytest
@@ -106,7 +107,7 @@ def test_silu_and_mul(dev, M, d):
     act.silu_and_mul(out, to_dev(x, dev))
     torch.cuda.synchronize()
     diff = ulp16_diff(np_of(out), want)
-    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    assert diff.max() <= 2 and (diff > 0).mean() < 1e-3
 
 
 def test_legacy_exports(dev):
