@@ -52,8 +52,8 @@ QS_API int qs_set_pdl(int enabled);
  *   out[m,n] = half( float(sum_k in[m,k]*q[n,k]) * wscales[n] * ascales[m] - w_szs[n] * a_ssums[m] )
  *   in_feats int8 [M,K]; kernel packed uint4 [N,K/2] in the checkpoint layout (w4a8_linear.py:292-322);
  *   wscales, w_szs fp16 [N]; ascales, a_ssums fp16 [M]; out fp16 [M,N].  N % 128 == 0, K % 128 == 0.
- *   workspace: qs_gemm_workspace_bytes() bytes, zero-initialised ONCE by the caller, then owned by the library
- *   (split-K tile counters are self-cleaning); may be NULL (then no split-K is used).
+ *   workspace: reserved (split-K partial tiles are exchanged through distributed shared memory inside a thread-block
+ *   cluster, no global scratch is needed); pass NULL / 0 or a buffer of qs_gemm_workspace_bytes() bytes.
  *   acc_out (optional, may be NULL): raw INT32 accumulators [M,N] for bit-exact parity checks.
  * --------------------------------------------------------------------------------------------------------- */
 QS_API int qs_w4a8_gemm_per_chn(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales, const void* w_szs,
@@ -73,8 +73,10 @@ QS_API int qs_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void
                  int32_t* acc_out, int M, int N, int K, void* workspace, size_t workspace_bytes, void* stream);
 
 QS_API size_t qs_gemm_workspace_bytes(void);
-/* test hook: force the stream-K decomposition (k-blocks of 128 per CTA) of the next GEMM calls; 0 = automatic */
-QS_API int qs_gemm_force_units_per_cta(int units);
+/* test hook: force the cluster split-K factor (1, 2, 4 or 8) of the next GEMM calls; 0 = automatic */
+QS_API int qs_gemm_force_split(int split);
+/* profiling hook: device buffer of 16 x uint64 per CTA receiving %globaltimer stamps of the GEMM phases; NULL disables */
+QS_API int qs_gemm_set_profile_buffer(void* dev_buffer);
 
 /* ---------------------------------------------------------------------------------------------------------
  * qserve_backend.fused_attention.single_query_attention         kernels/csrc/fused_attention/fused_attention.cpp:150-240

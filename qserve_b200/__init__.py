@@ -2,9 +2,8 @@
 
 `qserve_b200.backend` mirrors the reference's `qserve_backend` functions over the C ABI of
 `libqserve_b200.so` (include/qserve_b200.h); the top-level `qserve_backend` package re-exports them under
-the reference's module names.  Importing this package loads the shared library and fails if it is missing.
+the reference's module names.  Importing `qserve_b200.backend` (or `qserve_backend`) loads the shared library and
+fails loudly if it has not been built (`python -m qserve_b200.build`); there is no CPU fallback.
 """
-from . import _lib  # noqa: F401  (loads libqserve_b200.so; raises ImportError when it has not been built)
-
-__all__ = ["backend"]
+__all__ = ["backend", "build", "decode", "tp"]
 __version__ = "0.1.0"

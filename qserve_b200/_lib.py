@@ -21,7 +21,8 @@ SIGNATURES = {
     "qs_w4a8_gemm_per_group": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "qs_w8a8_gemm": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "qs_gemm_workspace_bytes": (c_size_t, []),
-    "qs_gemm_force_units_per_cta": (c_int, [_I]),
+    "qs_gemm_force_split": (c_int, [_I]),
+    "qs_gemm_set_profile_buffer": (c_int, [_P]),
     "qs_single_query_attention": (c_int, [_P, _P, _P, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P, _Z, _P]),
     "qs_attention_workspace_bytes": (c_size_t, [_I, _I, _I]),
     "qs_apply_bias_rope_update_kv_cache": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P]),

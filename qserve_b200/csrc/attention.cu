@@ -95,118 +95,136 @@ __device__ __forceinline__ uint32_t kv_quant_code(float x, float inv_s, float z)
   return r;
 }
 
-// per-chunk register staging of the raw page bytes
-template <int BITS>
-struct ChunkRegs {
-  // K: thread (g = lane/4, q = lane%4) holds dims [32q, 32q+32) of tokens g and 8+g
-  uint4 k[BITS == 4 ? 2 : 4];
-  // V: thread holds dims [16g, 16g+16) of tokens 2q, 2q+1, 2q+8, 2q+9
-  uint2 v4[BITS == 4 ? 4 : 1];
-  uint4 v8[BITS == 8 ? 4 : 1];
-  uint32_t ksz, vsz;  // lanes 0..15: packed (scale, aux) of token `lane` of the chunk
-};
+// ------------------------------------------------------------------------------------------------
+// K1: decode attention, TMA-staged (v2)
+//   stage = one 64-token page of one kv head: K codes | V codes | K scales | K zeros | V scales | V zeros, brought into
+//   shared memory by six cp.async.bulk copies issued by a dedicated producer warp (4-deep ring, mbarrier full/empty).
+//   Consumer warp w owns tokens [16w, 16w+16) of every page.
+//   Scale folding (exact in real arithmetic; skips the reference's per-element fp16 rounding of the dequantised values):
+//     q.k_t   = s_t * (q . u_t) + c_t * sum(q)          u = raw integer codes as fp16,   c_t = half(-s_t * z_t)
+//     sum_t p_t v_t = sum_t (p_t s_t) u_t + sum_t p_t c_t
+//   so the tensor-core operands are the raw codes and the per-token scale touches 4 logits / 4 probabilities per thread
+//   instead of 2 x 128 elements.  (KV8: k_t = s_t * (u_t - z_t), same folding with c_t = -s_t * z_t in fp32.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttnConsumers = 128;
+constexpr int kAttnThreadsV2 = kAttnConsumers + 32;
+constexpr int kPageTokens = 64;
+constexpr int kMaxBlocksSmem = 160;  // page pointers staged in shared memory (>= 8192 / 64 + slack)
 
 template <int BITS>
-__device__ __forceinline__ void load_chunk(ChunkRegs<BITS>& r, const long long* kptrs, const long long* vptrs, int t0, int tlen, int h,
-                                           const PageGeom& pg, int lane) {
-  const int g = lane >> 2, q = lane & 3;
-  const int blk = t0 / pg.tokens_per_block;
-  const int slot0 = t0 - blk * pg.tokens_per_block;
-  const uint8_t* kpage = reinterpret_cast<const uint8_t*>(kptrs[blk]);
-  const uint8_t* vpage = reinterpret_cast<const uint8_t*>(vptrs[blk]);
-  constexpr int kRowBytes = kD * BITS / 8;
-  const uint8_t* krow = kpage + static_cast<size_t>(h * pg.tokens_per_block + slot0) * kRowBytes;
-  const uint8_t* vrow = vpage + static_cast<size_t>(h * pg.tokens_per_block + slot0) * kRowBytes;
-  if constexpr (BITS == 4) {
-    r.k[0] = ldg_nc_128(krow + g * kRowBytes + q * 16);
-    r.k[1] = ldg_nc_128(krow + (8 + g) * kRowBytes + q * 16);
-    r.v4[0] = ldg_nc_64(vrow + (2 * q) * kRowBytes + g * 8);
-    r.v4[1] = ldg_nc_64(vrow + (2 * q + 1) * kRowBytes + g * 8);
-    r.v4[2] = ldg_nc_64(vrow + (2 * q + 8) * kRowBytes + g * 8);
-    r.v4[3] = ldg_nc_64(vrow + (2 * q + 9) * kRowBytes + g * 8);
-  } else {
-    r.k[0] = ldg_nc_128(krow + g * kRowBytes + q * 32);
-    r.k[1] = ldg_nc_128(krow + g * kRowBytes + q * 32 + 16);
-    r.k[2] = ldg_nc_128(krow + (8 + g) * kRowBytes + q * 32);
-    r.k[3] = ldg_nc_128(krow + (8 + g) * kRowBytes + q * 32 + 16);
-    r.v8[0] = ldg_nc_128(vrow + (2 * q) * kRowBytes + g * 16);
-    r.v8[1] = ldg_nc_128(vrow + (2 * q + 1) * kRowBytes + g * 16);
-    r.v8[2] = ldg_nc_128(vrow + (2 * q + 8) * kRowBytes + g * 16);
-    r.v8[3] = ldg_nc_128(vrow + (2 * q + 9) * kRowBytes + g * 16);
-  }
-  // scale / zero of token (t0 + lane) for lanes 0..15; scales fp16 [Hkv][64], zeros fp16 [Hkv][64] after the codes
-  const int tl = lane & 15;
-  const __half* ks = reinterpret_cast<const __half*>(kpage + pg.code_bytes) + h * pg.tokens_per_block + slot0 + tl;
-  const __half* vs = reinterpret_cast<const __half*>(vpage + pg.code_bytes) + h * pg.tokens_per_block + slot0 + tl;
-  const int zoff = pg.num_kv_heads * pg.tokens_per_block;
-  const __half s_k = __ldg(ks), z_k = __ldg(ks + zoff), s_v = __ldg(vs), z_v = __ldg(vs + zoff);
-  if constexpr (BITS == 4) {
-    // aux = half(-float(s) * float(z))   (Utils.h:2203-2204)
-    r.ksz = pack_h2(s_k, __float2half_rn(__fmul_rn(-__half2float(s_k), __half2float(z_k))));
-    r.vsz = pack_h2(s_v, __float2half_rn(__fmul_rn(-__half2float(s_v), __half2float(z_v))));
-  } else {
-    r.ksz = pack_h2(s_k, z_k);
-    r.vsz = pack_h2(s_v, z_v);
-  }
-  // slots at or beyond tlen are unwritten (or being written by the owner CTA): force a finite (zero) dequant so that
-  // p = 0 times V can never produce NaN; their logits are masked to -inf separately
-  if (t0 + tl >= tlen) r.ksz = r.vsz = 0u;
+struct StageLayout {
+  static constexpr int kCodes = kPageTokens * kD * BITS / 8;  // bytes of K (or V) codes of one head-page
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = kCodes;
+  static constexpr int kOffKs = 2 * kCodes;      // fp16 [64]
+  static constexpr int kOffKz = kOffKs + 128;
+  static constexpr int kOffVs = kOffKz + 128;
+  static constexpr int kOffVz = kOffVs + 128;
+  static constexpr int kBytes = kOffVz + 128;
+  static constexpr int kStages = (BITS == 4) ? 4 : 3;
+};
+
+// mma.sync m16n8k16 with explicit accumulator registers (rows 8..15 of A are zero)
+__device__ __forceinline__ void mma16816_acc(float& c0, float& c1, float& c2, float& c3, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
 
-// 8-bit dequant of one element: half( float(s) * (float(u) - float(z)) )   (Utils.h:2095-2107)
-__device__ __forceinline__ float deq8(uint32_t u, float s, float z) { return __fmul_rn(s, __fsub_rn(static_cast<float>(u), z)); }
-
-struct SoftmaxState {
-  float m, l;
-};
-
 template <int BITS>
-__global__ void __launch_bounds__(kAttnThreads, 3)
+__global__ void __launch_bounds__(kAttnThreadsV2, 4)
 decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restrict__ k_in, const __half* __restrict__ v_in, long long q_stride,
                         long long k_stride, long long v_stride, const long long* __restrict__ kv_pointers, const int* __restrict__ lengths,
                         __half* __restrict__ out, int num_heads, int num_kv_heads, int max_blocks, PageGeom pg, float rotary_base, int rotary_dim,
                         int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt) {
-  const int G = num_heads / num_kv_heads;           // query heads per kv head
+  using SL = StageLayout<BITS>;
+  constexpr int R = SL::kStages;
+  const int G = num_heads / num_kv_heads;
   const int gparts = (G + kMaxG - 1) / kMaxG;
-  const int hk = blockIdx.x / gparts;               // kv head
+  const int hk = blockIdx.x / gparts;
   const int gpart = blockIdx.x - hk * gparts;
-  const int h0 = hk * G + gpart * kMaxG;            // first query head of this CTA
-  const int Gc = min(kMaxG, G - gpart * kMaxG);     // query heads handled here
+  const int h0 = hk * G + gpart * kMaxG;
+  const int Gc = min(kMaxG, G - gpart * kMaxG);
   const int b = blockIdx.y;
   const int split = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q4 = lane & 3;
 
-  __shared__ __align__(16) __half s_q[kMaxG * kD];   // rotated q
-  __shared__ __align__(16) __half s_k[kD];           // rotated new k
-  __shared__ __align__(16) __half s_v[kD];           // new v
-  __shared__ float s_cs[kD];                         // cos | sin for the 64 frequencies
+  extern __shared__ __align__(128) uint8_t smem_attn[];
+  uint8_t* s_ring = smem_attn;                                           // R stages
+  float* s_o = reinterpret_cast<float*>(smem_attn);                      // merge buffer [4][8][128], aliases the ring at the end
+  __shared__ __align__(16) __half s_q[kMaxG * kD];
+  __shared__ __align__(16) __half s_k[kD];
+  __shared__ __align__(16) __half s_v[kD];
+  __shared__ float s_cs[kD];
   __shared__ float s_m[kWarps + 1][kMaxG], s_l[kWarps + 1][kMaxG];
-  __shared__ __align__(16) float s_o[kWarps][kMaxG][kD];
+  __shared__ long long s_kp[kMaxBlocksSmem], s_vp[kMaxBlocksSmem];
+  __shared__ uint32_t s_meta[R][2][kPageTokens];                         // per token packed (s, c) for K and V
+  __shared__ __align__(8) uint64_t s_full[R], s_empty[R];
   __shared__ uint32_t s_last;
 
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < R; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], kWarps);
+    }
+    fence_barrier_init();
+  }
   pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
 
   const int tlen = (lengths ? lengths[b] : timestep) - 1;  // tokens already in the cache (Template.hpp:901)
   const long long* kptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 0) * max_blocks;
   const long long* vptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 1) * max_blocks;
+  const int n_pages = (tlen + kPageTokens - 1) / kPageTokens;
+  const int pps = (n_pages + nsplit - 1) / nsplit;
+  const int p_begin = split * pps, p_end = min(n_pages, p_begin + pps);
+  const int last_blk = tlen / pg.tokens_per_block;  // page receiving the new token
+  for (int i = threadIdx.x; i <= last_blk && i < kMaxBlocksSmem; i += kAttnThreadsV2) {
+    s_kp[i] = kptrs[i];
+    s_vp[i] = vptrs[i];
+  }
+  __syncthreads();
 
-  // ---------------- new token: load, RoPE (NeoX, position tlen), stage in shared memory ----------------
-  {
+  if (warp == kWarps) {
+    // ================================ producer warp: stream this split's pages ================================
+    if (lane == 0) {
+      const int zoff = pg.num_kv_heads * pg.tokens_per_block * 2;  // bytes from a scale row to the zero row
+      int s = 0;
+      uint32_t ph = 0;
+      for (int pidx = p_begin; pidx < p_end; ++pidx) {
+        if (pidx - p_begin >= R) mbar_wait(&s_empty[s], ph ^ 1);
+        const uint8_t* kpage = reinterpret_cast<const uint8_t*>(s_kp[pidx]);
+        const uint8_t* vpage = reinterpret_cast<const uint8_t*>(s_vp[pidx]);
+        uint8_t* dst = s_ring + s * SL::kBytes;
+        mbar_expect_tx(&s_full[s], SL::kBytes);
+        bulk_copy_g2s(dst + SL::kOffK, kpage + static_cast<size_t>(hk) * SL::kCodes, SL::kCodes, &s_full[s]);
+        bulk_copy_g2s(dst + SL::kOffV, vpage + static_cast<size_t>(hk) * SL::kCodes, SL::kCodes, &s_full[s]);
+        const uint8_t* kmeta = kpage + pg.code_bytes + hk * 128;
+        const uint8_t* vmeta = vpage + pg.code_bytes + hk * 128;
+        bulk_copy_g2s(dst + SL::kOffKs, kmeta, 128, &s_full[s]);
+        bulk_copy_g2s(dst + SL::kOffKz, kmeta + zoff, 128, &s_full[s]);
+        bulk_copy_g2s(dst + SL::kOffVs, vmeta, 128, &s_full[s]);
+        bulk_copy_g2s(dst + SL::kOffVz, vmeta + zoff, 128, &s_full[s]);
+        if (++s == R) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ================================ consumer warps ================================
+    // ---- new token: RoPE (NeoX, position tlen) of q and k; stage q, k, v in shared memory ----
     const int half_rot = rotary_dim / 2;
     if (threadIdx.x < half_rot) {
-      // inv_freq = t / base^(2i/rot)   (Utils.h:1147-1152), accurate powf / sincosf
       const float inv_freq = __fdiv_rn(static_cast<float>(tlen), powf(rotary_base, __fdiv_rn(static_cast<float>(2 * threadIdx.x), static_cast<float>(rotary_dim))));
       float sn, cs;
       sincosf(inv_freq, &sn, &cs);
       s_cs[threadIdx.x] = cs;
       s_cs[half_rot + threadIdx.x] = sn;
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     const __half* kg = k_in + static_cast<size_t>(b) * k_stride + static_cast<size_t>(hk) * kD;
     const __half* vg = v_in + static_cast<size_t>(b) * v_stride + static_cast<size_t>(hk) * kD;
-    for (int idx = threadIdx.x; idx < (Gc + 1) * (kD / 2); idx += kAttnThreads) {
+    for (int idx = threadIdx.x; idx < (Gc + 1) * (kD / 2); idx += kAttnConsumers) {
       const int r = idx / (kD / 2), i = idx - r * (kD / 2);  // r == Gc -> the k row
       const __half* src = (r < Gc) ? (q_in + static_cast<size_t>(b) * q_stride + static_cast<size_t>(h0 + r) * kD) : kg;
       __half* dst = (r < Gc) ? (s_q + r * kD) : s_k;
@@ -215,263 +233,301 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       dst[i] = __float2half_rn(__fsub_rn(__fmul_rn(c, x0), __fmul_rn(s, x1)));
       dst[i + half_rot] = __float2half_rn(__fadd_rn(__fmul_rn(c, x1), __fmul_rn(s, x0)));
     }
-    for (int i = threadIdx.x; i < kD; i += kAttnThreads) s_v[i] = vg[i];
-    for (int i = threadIdx.x + Gc * kD; i < kMaxG * kD; i += kAttnThreads) s_q[i] = __float2half_rn(0.f);
-    __syncthreads();
-  }
+    for (int i = threadIdx.x; i < kD; i += kAttnConsumers) s_v[i] = vg[i];
+    for (int i = threadIdx.x + Gc * kD; i < kMaxG * kD; i += kAttnConsumers) s_q[i] = __float2half_rn(0.f);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
 
-  // ---------------- quantise + append the new K/V (one CTA per kv head: split 0, first head group) ----------------
-  const bool owner = (split == 0);
-  if (owner && gpart == 0 && warp < 2) {
-    const __half* src = (warp == 0) ? s_k : s_v;
-    const long long* ptrs = (warp == 0) ? kptrs : vptrs;
-    const float L = (BITS == 4) ? 15.f : 255.f;
-    float x[4];
+    // ---- quantise + append the new K / V (one CTA per kv head) ----
+    const bool owner_w = (split == 0) && (gpart == 0);
+    if (owner_w && warp < 2) {
+      const __half* src = (warp == 0) ? s_k : s_v;
+      const float L = (BITS == 4) ? 15.f : 255.f;
+      float x[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = __half2float(src[lane * 4 + j]);
-    float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), mn = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
+      for (int j = 0; j < 4; ++j) x[j] = __half2float(src[lane * 4 + j]);
+      float mx = fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), mn = fminf(fminf(x[0], x[1]), fminf(x[2], x[3]));
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
-    }
-    __half sc, zp;
-    kv_quant_params(mx, mn, L, sc, zp);
-    const float inv_s = __fdiv_rn(1.0f, __half2float(sc)), zf = __half2float(zp);
-    const int blk = tlen / pg.tokens_per_block, slot = tlen - blk * pg.tokens_per_block;
-    uint8_t* page = reinterpret_cast<uint8_t*>(ptrs[blk]);
-    uint32_t c[4];
+      for (int m = 16; m >= 1; m >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+      }
+      __half sc, zp;
+      kv_quant_params(mx, mn, L, sc, zp);
+      const float inv_s = __fdiv_rn(1.0f, __half2float(sc)), zf = __half2float(zp);
+      const int slot = tlen - last_blk * pg.tokens_per_block;
+      uint8_t* page = reinterpret_cast<uint8_t*>((warp == 0) ? kptrs[last_blk] : vptrs[last_blk]);
+      uint32_t c[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = kv_quant_code(x[j], inv_s, zf);
-    if constexpr (BITS == 4) {
-      const uint16_t packed = static_cast<uint16_t>((c[0] & 0xF) | ((c[1] & 0xF) << 4) | ((c[2] & 0xF) << 8) | ((c[3] & 0xF) << 12));
-      reinterpret_cast<uint16_t*>(page + static_cast<size_t>(hk * pg.tokens_per_block + slot) * (kD / 2))[lane] = packed;
-    } else {
-      reinterpret_cast<uint32_t*>(page + static_cast<size_t>(hk * pg.tokens_per_block + slot) * kD)[lane] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
-    }
-    if (lane == 0) {
-      __half* meta = reinterpret_cast<__half*>(page + pg.code_bytes);
-      meta[hk * pg.tokens_per_block + slot] = sc;
-      meta[pg.num_kv_heads * pg.tokens_per_block + hk * pg.tokens_per_block + slot] = zp;
-    }
-  }
-
-  // ---------------- Q operand fragments (permuted to match the in-register dequant order) ----------------
-  // KV4: k-step 2w uses dims d0+{0,4 | 1,5}, k-step 2w+1 dims d0+{2,6 | 3,7}, d0 = 32*q4 + 8w  (nibble pairs of the lop3 trick)
-  // KV8: k-step s  uses dims d0+{0,1 | 2,3},  d0 = 32*q4 + 4s
-  uint32_t qa0[8], qa2[8];
-  {
-    const __half* qr = s_q + g * kD + 32 * q4;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
+      for (int j = 0; j < 4; ++j) c[j] = kv_quant_code(x[j], inv_s, zf);
       if constexpr (BITS == 4) {
-        const int d0 = 8 * (s >> 1) + 2 * (s & 1);
-        qa0[s] = pack_h2(qr[d0], qr[d0 + 4]);
-        qa2[s] = pack_h2(qr[d0 + 1], qr[d0 + 5]);
+        const uint16_t packed = static_cast<uint16_t>((c[0] & 0xF) | ((c[1] & 0xF) << 4) | ((c[2] & 0xF) << 8) | ((c[3] & 0xF) << 12));
+        reinterpret_cast<uint16_t*>(page + static_cast<size_t>(hk * pg.tokens_per_block + slot) * (kD / 2))[lane] = packed;
       } else {
-        qa0[s] = pack_h2(qr[4 * s], qr[4 * s + 1]);
-        qa2[s] = pack_h2(qr[4 * s + 2], qr[4 * s + 3]);
+        reinterpret_cast<uint32_t*>(page + static_cast<size_t>(hk * pg.tokens_per_block + slot) * kD)[lane] = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
+      }
+      if (lane == 0) {
+        __half* meta = reinterpret_cast<__half*>(page + pg.code_bytes);
+        meta[hk * pg.tokens_per_block + slot] = sc;
+        meta[pg.num_kv_heads * pg.tokens_per_block + hk * pg.tokens_per_block + slot] = zp;
       }
     }
-  }
 
-  // ---------------- stream this split's share of the cached tokens ----------------
-  const float sm_scale = rsqrtf(static_cast<float>(kD)) * 1.4426950408889634f;  // 1/sqrt(D) * log2(e)
-  const int n_chunks = (tlen + kChunk - 1) / kChunk;
-  const int cps = (n_chunks + nsplit - 1) / nsplit;
-  const int c_begin = split * cps, c_end = min(n_chunks, c_begin + cps);
-
-  float o[16][2];
-  float odummy[2] = {0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 16; ++j) o[j][0] = o[j][1] = 0.f;
-  float m_run = -CUDART_INF_F, l_run = 0.f;
-
-  ChunkRegs<BITS> cur, nxt;
-  int c = c_begin + warp;
-  if (c < c_end) load_chunk<BITS>(cur, kptrs, vptrs, c * kChunk, tlen, hk, pg, lane);
-  for (; c < c_end; c += kWarps) {
-    const int cn = c + kWarps;
-    if (cn < c_end) load_chunk<BITS>(nxt, kptrs, vptrs, cn * kChunk, tlen, hk, pg, lane);
-    const int t0 = c * kChunk;
-
-    // ---- S = Q K^T for 2 n-tiles of 8 tokens ----
-    float sacc[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-      const uint32_t sz = __shfl_sync(0xffffffffu, cur.ksz, nt * 8 + g);
-      if constexpr (BITS == 4) {
-        const uint32_t s2 = __byte_perm(sz, 0, 0x1010), c2 = __byte_perm(sz, 0, 0x3232);
-        const uint32_t wds[4] = {cur.k[nt].x, cur.k[nt].y, cur.k[nt].z, cur.k[nt].w};
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const uint32_t x = wds[w], top = x >> 8;
-          uint32_t e0 = h2_sub(lop3_and_or(x, 0x000f000fu, kMagic), kMagic);
-          uint32_t e1 = h2_fma(lop3_and_or(x, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-          uint32_t e2 = h2_sub(lop3_and_or(top, 0x000f000fu, kMagic), kMagic);
-          uint32_t e3 = h2_fma(lop3_and_or(top, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-          e0 = h2_fma(e0, s2, c2); e1 = h2_fma(e1, s2, c2); e2 = h2_fma(e2, s2, c2); e3 = h2_fma(e3, s2, c2);
-          mma16816(sacc[nt], qa0[2 * w], qa2[2 * w], e0, e1);
-          mma16816(sacc[nt], qa0[2 * w + 1], qa2[2 * w + 1], e2, e3);
-        }
-      } else {
-        const float sf = __half2float(__ushort_as_half(static_cast<uint16_t>(sz & 0xFFFF)));
-        const float zf = __half2float(__ushort_as_half(static_cast<uint16_t>(sz >> 16)));
-        const uint32_t wds[8] = {cur.k[2 * nt].x, cur.k[2 * nt].y, cur.k[2 * nt].z, cur.k[2 * nt].w,
-                                 cur.k[2 * nt + 1].x, cur.k[2 * nt + 1].y, cur.k[2 * nt + 1].z, cur.k[2 * nt + 1].w};
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const uint32_t x = wds[s];
-          const uint32_t b0 = pack_f2h2(deq8(x & 0xFF, sf, zf), deq8((x >> 8) & 0xFF, sf, zf));
-          const uint32_t b1 = pack_f2h2(deq8((x >> 16) & 0xFF, sf, zf), deq8(x >> 24, sf, zf));
-          mma16816(sacc[nt], qa0[s], qa2[s], b0, b1);
-        }
-      }
-    }
-    // ---- online softmax for row g (tokens t0 + nt*8 + 2*q4 + {0,1}) ----
-    float p[2][2];
-    float cmax = -CUDART_INF_F;
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int t = t0 + nt * 8 + 2 * q4 + j;
-        p[nt][j] = (t < tlen) ? sacc[nt][j] * sm_scale : -CUDART_INF_F;
-        cmax = fmaxf(cmax, p[nt][j]);
-      }
-    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
-    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
-    const float m_new = fmaxf(m_run, cmax);
-    const float alpha = exp2f(m_run - m_new);
-    m_run = m_new;
-    float psum = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        p[nt][j] = exp2f(p[nt][j] - m_new);
-        psum += p[nt][j];
-      }
-    l_run = l_run * alpha + psum;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      o[j][0] *= alpha;
-      o[j][1] *= alpha;
-    }
-    const uint32_t pa0 = pack_f2h2(p[0][0], p[0][1]);  // tokens 2q, 2q+1
-    const uint32_t pa2 = pack_f2h2(p[1][0], p[1][1]);  // tokens 2q+8, 2q+9
-
-    // ---- O += P V ; n-tile j <-> dims 16*g' + j of thread group g' ----
+    // ---- Q operand fragments, permuted to the in-register order of the unpacked codes; sum(q) per row ----
+    uint32_t qa0[8], qa2[8];
+    float sumq;
     {
-      const uint32_t szA = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4), szB = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4 + 1);
-      const uint32_t szC = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4 + 8), szD = __shfl_sync(0xffffffffu, cur.vsz, 2 * q4 + 9);
-      if constexpr (BITS == 4) {
-        const uint32_t s01 = __byte_perm(szA, szB, 0x5410), c01 = __byte_perm(szA, szB, 0x7632);  // (sA,sB), (cA,cB)
-        const uint32_t s89 = __byte_perm(szC, szD, 0x5410), c89 = __byte_perm(szC, szD, 0x7632);
-#pragma unroll
-        for (int ww = 0; ww < 2; ++ww) {
-          const uint32_t a = ww ? cur.v4[0].y : cur.v4[0].x, bb = ww ? cur.v4[1].y : cur.v4[1].x;
-          const uint32_t cc = ww ? cur.v4[2].y : cur.v4[2].x, dd = ww ? cur.v4[3].y : cur.v4[3].x;
-#pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t sel = static_cast<uint32_t>(kb) | (static_cast<uint32_t>(kb) << 4) | (static_cast<uint32_t>(4 + kb) << 8) |
-                                 (static_cast<uint32_t>(4 + kb) << 12);  // bytes [a_kb, a_kb, b_kb, b_kb]
-            const uint32_t m01 = __byte_perm(a, bb, sel), m89 = __byte_perm(cc, dd, sel);
-            uint32_t lo01 = h2_sub(lop3_and_or(m01, 0x000f000fu, kMagic), kMagic);
-            uint32_t hi01 = h2_fma(lop3_and_or(m01, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-            uint32_t lo89 = h2_sub(lop3_and_or(m89, 0x000f000fu, kMagic), kMagic);
-            uint32_t hi89 = h2_fma(lop3_and_or(m89, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-            lo01 = h2_fma(lo01, s01, c01); hi01 = h2_fma(hi01, s01, c01);
-            lo89 = h2_fma(lo89, s89, c89); hi89 = h2_fma(hi89, s89, c89);
-            const int j = 8 * ww + 2 * kb;
-            float acc0[4] = {o[j][0], o[j][1], odummy[0], odummy[1]};
-            mma16816(acc0, pa0, pa2, lo01, lo89);
-            o[j][0] = acc0[0]; o[j][1] = acc0[1];
-            float acc1[4] = {o[j + 1][0], o[j + 1][1], odummy[0], odummy[1]};
-            mma16816(acc1, pa0, pa2, hi01, hi89);
-            o[j + 1][0] = acc1[0]; o[j + 1][1] = acc1[1];
-          }
-        }
-      } else {
-        const float sA = __half2float(__ushort_as_half(static_cast<uint16_t>(szA & 0xFFFF))), zA = __half2float(__ushort_as_half(static_cast<uint16_t>(szA >> 16)));
-        const float sB = __half2float(__ushort_as_half(static_cast<uint16_t>(szB & 0xFFFF))), zB = __half2float(__ushort_as_half(static_cast<uint16_t>(szB >> 16)));
-        const float sC = __half2float(__ushort_as_half(static_cast<uint16_t>(szC & 0xFFFF))), zC = __half2float(__ushort_as_half(static_cast<uint16_t>(szC >> 16)));
-        const float sD = __half2float(__ushort_as_half(static_cast<uint16_t>(szD & 0xFFFF))), zD = __half2float(__ushort_as_half(static_cast<uint16_t>(szD >> 16)));
-        const uint32_t wa[4] = {cur.v8[0].x, cur.v8[0].y, cur.v8[0].z, cur.v8[0].w};
-        const uint32_t wb[4] = {cur.v8[1].x, cur.v8[1].y, cur.v8[1].z, cur.v8[1].w};
-        const uint32_t wc[4] = {cur.v8[2].x, cur.v8[2].y, cur.v8[2].z, cur.v8[2].w};
-        const uint32_t wd[4] = {cur.v8[3].x, cur.v8[3].y, cur.v8[3].z, cur.v8[3].w};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int sh = 8 * (j & 3);
-          const uint32_t b0 = pack_f2h2(deq8((wa[j >> 2] >> sh) & 0xFF, sA, zA), deq8((wb[j >> 2] >> sh) & 0xFF, sB, zB));
-          const uint32_t b1 = pack_f2h2(deq8((wc[j >> 2] >> sh) & 0xFF, sC, zC), deq8((wd[j >> 2] >> sh) & 0xFF, sD, zD));
-          float acc0[4] = {o[j][0], o[j][1], odummy[0], odummy[1]};
-          mma16816(acc0, pa0, pa2, b0, b1);
-          o[j][0] = acc0[0]; o[j][1] = acc0[1];
-        }
-      }
-    }
-    if (cn < c_end) cur = nxt;
-  }
-
-  // ---------------- merge the warps (and the un-quantised new token) inside the CTA ----------------
-  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-  if (q4 == 0) {
-    s_m[warp][g] = m_run;
-    s_l[warp][g] = l_run;
-  }
-  // thread (g, q4) holds row g, dims 32*q4 + 16*e + j  (e = 0,1 ; j = 0..15)
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    s_o[warp][g][32 * q4 + j] = o[j][0];
-    s_o[warp][g][32 * q4 + 16 + j] = o[j][1];
-  }
-  // new token logit: fp32 dot of the rotated, un-quantised q and k  (Template.hpp:1410-1441)
-  if (owner) {
-    for (int r = warp; r < Gc; r += kWarps) {
+      const __half* qr = s_q + g * kD + 32 * q4;
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc = fmaf(__half2float(s_q[r * kD + lane * 4 + j]), __half2float(s_k[lane * 4 + j]), acc);
+      for (int j = 0; j < 32; ++j) acc += __half2float(qr[j]);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      sumq = acc;
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-      if (lane == 0) {
-        s_m[kWarps][r] = acc * sm_scale;
-        s_l[kWarps][r] = 1.f;
+      for (int s = 0; s < 8; ++s) {
+        if constexpr (BITS == 4) {
+          const int d0 = 8 * (s >> 1) + 2 * (s & 1);  // k-step 2w: nibbles (0,4 | 1,5); 2w+1: (2,6 | 3,7) of word w
+          qa0[s] = pack_h2(qr[d0], qr[d0 + 4]);
+          qa2[s] = pack_h2(qr[d0 + 1], qr[d0 + 5]);
+        } else {
+          qa0[s] = pack_h2(qr[4 * s], qr[4 * s + 1]);
+          qa2[s] = pack_h2(qr[4 * s + 2], qr[4 * s + 3]);
+        }
+      }
+    }
+
+    const float sm_scale = rsqrtf(static_cast<float>(kD)) * 1.4426950408889634f;  // 1/sqrt(D) * log2(e)
+    float o[16][2];
+    float od0 = 0.f, od1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j][0] = o[j][1] = 0.f;
+    float m_run = -CUDART_INF_F, l_run = 0.f, c_run = 0.f;  // running max (log2 units), sum of p, sum of p * c_v
+
+    // S column c of n-tile nt <-> chunk token nt*8 + (c&1)*4 + (c>>1)   (keeps the V row reads at a 2-way bank conflict)
+    const int tokA = (g & 1) * 4 + (g >> 1);       // K row this lane loads for n-tile 0 (n-tile 1: + 8)
+    const int c0 = 2 * q4, c1 = 2 * q4 + 1;        // this lane's S / P columns
+    const int tk0 = (c0 & 1) * 4 + (c0 >> 1), tk1 = (c1 & 1) * 4 + (c1 >> 1);  // tokens of columns c0, c1 inside an n-tile
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pidx = p_begin; pidx < p_end; ++pidx) {
+      mbar_wait(&s_full[s], ph);
+      const uint8_t* st = s_ring + s * SL::kBytes;
+      const int t0 = pidx * kPageTokens + warp * kChunk;  // first token of this warp's chunk
+      if (t0 < tlen) {
+        // per-token (scale, aux) pairs: lanes 0..15 -> K tokens, lanes 16..31 -> V tokens of the chunk
+        {
+          const int tl = lane & 15;
+          const __half* sp = reinterpret_cast<const __half*>(st + (lane < 16 ? SL::kOffKs : SL::kOffVs)) + warp * kChunk + tl;
+          const __half sc = sp[0], zp = sp[64];
+          uint32_t packed;
+          if constexpr (BITS == 4) packed = pack_h2(sc, __float2half_rn(__fmul_rn(-__half2float(sc), __half2float(zp))));
+          else packed = pack_h2(sc, zp);
+          if (t0 + tl >= tlen) packed = 0u;  // unwritten slots: force finite zeros (their logits are masked below)
+          s_meta[s][lane >> 4][warp * kChunk + tl] = packed;
+        }
+        __syncwarp();
+        // ---- S = Q K^T on raw codes ----
+        float sacc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+          const uint8_t* krow = st + SL::kOffK + (warp * kChunk + nt * 8 + tokA) * (kD * BITS / 8);
+          if constexpr (BITS == 4) {
+            const uint4 kv = *reinterpret_cast<const uint4*>(krow + q4 * 16);
+            const uint32_t wds[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const uint32_t x = wds[w], top = x >> 8;
+              const uint32_t e0 = h2_sub(lop3_and_or(x, 0x000f000fu, kMagic), kMagic);
+              const uint32_t e1 = h2_fma(lop3_and_or(x, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+              const uint32_t e2 = h2_sub(lop3_and_or(top, 0x000f000fu, kMagic), kMagic);
+              const uint32_t e3 = h2_fma(lop3_and_or(top, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+              mma16816_acc(sacc[nt][0], sacc[nt][1], sacc[nt][2], sacc[nt][3], qa0[2 * w], qa2[2 * w], e0, e1);
+              mma16816_acc(sacc[nt][0], sacc[nt][1], sacc[nt][2], sacc[nt][3], qa0[2 * w + 1], qa2[2 * w + 1], e2, e3);
+            }
+          } else {
+            const uint4 ka = *reinterpret_cast<const uint4*>(krow + q4 * 32);
+            const uint4 kb = *reinterpret_cast<const uint4*>(krow + q4 * 32 + 16);
+            const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              // bytes -> fp16 integers: 0x6400 | u  = 1024 + u, minus 1024 (exact)
+              const uint32_t e0 = h2_sub(__byte_perm(wds[w], kMagic, 0x7150), kMagic);
+              const uint32_t e1 = h2_sub(__byte_perm(wds[w], kMagic, 0x7352), kMagic);
+              mma16816_acc(sacc[nt][0], sacc[nt][1], sacc[nt][2], sacc[nt][3], qa0[w], qa2[w], e0, e1);
+            }
+          }
+        }
+        // ---- logits (log2 units) for row g, columns c0, c1 of both n-tiles; online softmax with lazy rescale ----
+        float t[2][2];
+        float cmax = -CUDART_INF_F;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const uint32_t m0 = s_meta[s][0][warp * kChunk + nt * 8 + tk0], m1 = s_meta[s][0][warp * kChunk + nt * 8 + tk1];
+          float sc0, sc1, cc0, cc1;
+          sc0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 & 0xFFFF)));
+          sc1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 & 0xFFFF)));
+          if constexpr (BITS == 4) {
+            cc0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
+            cc1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
+          } else {
+            cc0 = -sc0 * __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
+            cc1 = -sc1 * __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
+          }
+          const bool ok0 = (t0 + nt * 8 + tk0) < tlen, ok1 = (t0 + nt * 8 + tk1) < tlen;
+          t[nt][0] = ok0 ? (sc0 * sacc[nt][0] + cc0 * sumq) * sm_scale : -CUDART_INF_F;
+          t[nt][1] = ok1 ? (sc1 * sacc[nt][1] + cc1 * sumq) * sm_scale : -CUDART_INF_F;
+          cmax = fmaxf(cmax, fmaxf(t[nt][0], t[nt][1]));
+        }
+        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
+        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
+        const bool need = cmax > m_run + 8.f;  // rescale only when the running max moves by more than 2^8
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m_run - cmax) : 1.f;
+          if (need) m_run = cmax;
+          l_run *= alpha;
+          c_run *= alpha;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            o[j][0] *= alpha;
+            o[j][1] *= alpha;
+          }
+        }
+        // ---- P' = p * s_v ;  c_run += p * c_v ----
+        uint32_t pa[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const uint32_t m0 = s_meta[s][1][warp * kChunk + nt * 8 + tk0], m1 = s_meta[s][1][warp * kChunk + nt * 8 + tk1];
+          const float p0 = exp2f(t[nt][0] - m_run), p1 = exp2f(t[nt][1] - m_run);
+          const float sv0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 & 0xFFFF)));
+          const float sv1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 & 0xFFFF)));
+          float cv0, cv1;
+          if constexpr (BITS == 4) {
+            cv0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
+            cv1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
+          } else {
+            cv0 = -sv0 * __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
+            cv1 = -sv1 * __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
+          }
+          l_run += p0 + p1;
+          c_run += p0 * cv0 + p1 * cv1;
+          pa[nt] = pack_f2h2(p0 * sv0, p1 * sv1);
+        }
+        // ---- O += P' V on raw codes; MMA k index (2q4, 2q4+1 | +8) <-> S columns c0, c1 of n-tile 0 | 1 ----
+        {
+          const uint8_t* vbase = st + SL::kOffV + (warp * kChunk) * (kD * BITS / 8);
+          if constexpr (BITS == 4) {
+            const uint2 va = *reinterpret_cast<const uint2*>(vbase + tk0 * 64 + g * 8);
+            const uint2 vb = *reinterpret_cast<const uint2*>(vbase + tk1 * 64 + g * 8);
+            const uint2 vc = *reinterpret_cast<const uint2*>(vbase + (8 + tk0) * 64 + g * 8);
+            const uint2 vd = *reinterpret_cast<const uint2*>(vbase + (8 + tk1) * 64 + g * 8);
+#pragma unroll
+            for (int ww = 0; ww < 2; ++ww) {
+              const uint32_t a = ww ? va.y : va.x, bb = ww ? vb.y : vb.x, cc = ww ? vc.y : vc.x, dd = ww ? vd.y : vd.x;
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {
+                const uint32_t sel = static_cast<uint32_t>(kb) | (static_cast<uint32_t>(kb) << 4) | (static_cast<uint32_t>(4 + kb) << 8) |
+                                     (static_cast<uint32_t>(4 + kb) << 12);  // bytes [a_kb, a_kb, b_kb, b_kb]
+                const uint32_t m01 = __byte_perm(a, bb, sel), m89 = __byte_perm(cc, dd, sel);
+                const uint32_t lo01 = h2_sub(lop3_and_or(m01, 0x000f000fu, kMagic), kMagic);
+                const uint32_t hi01 = h2_fma(lop3_and_or(m01, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+                const uint32_t lo89 = h2_sub(lop3_and_or(m89, 0x000f000fu, kMagic), kMagic);
+                const uint32_t hi89 = h2_fma(lop3_and_or(m89, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
+                const int j = 8 * ww + 2 * kb;
+                mma16816_acc(o[j][0], o[j][1], od0, od1, pa[0], pa[1], lo01, lo89);
+                mma16816_acc(o[j + 1][0], o[j + 1][1], od0, od1, pa[0], pa[1], hi01, hi89);
+              }
+            }
+          } else {
+            const uint4 va = *reinterpret_cast<const uint4*>(vbase + tk0 * 128 + g * 16);
+            const uint4 vb = *reinterpret_cast<const uint4*>(vbase + tk1 * 128 + g * 16);
+            const uint4 vc = *reinterpret_cast<const uint4*>(vbase + (8 + tk0) * 128 + g * 16);
+            const uint4 vd = *reinterpret_cast<const uint4*>(vbase + (8 + tk1) * 128 + g * 16);
+            const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+            const uint32_t wc[4] = {vc.x, vc.y, vc.z, vc.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              // byte j of rows (a, b) -> half2(1024 + a_j, 1024 + b_j) - 1024
+              const uint32_t sel = static_cast<uint32_t>(j & 3) | 0x0080u | (static_cast<uint32_t>(4 + (j & 3)) << 8) | 0x8000u;
+              uint32_t b0 = __byte_perm(wa[j >> 2], wb[j >> 2], sel) | kMagic;
+              uint32_t b1 = __byte_perm(wc[j >> 2], wd[j >> 2], sel) | kMagic;
+              b0 = h2_sub(b0, kMagic);
+              b1 = h2_sub(b1, kMagic);
+              mma16816_acc(o[j][0], o[j][1], od0, od1, pa[0], pa[1], b0, b1);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+      if (++s == R) { s = 0; ph ^= 1; }
+    }
+
+    // ---- per-warp partials -> shared memory (the ring is free: every stage of this CTA has been consumed) ----
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    c_run += __shfl_xor_sync(0xffffffffu, c_run, 1);
+    c_run += __shfl_xor_sync(0xffffffffu, c_run, 2);
+    if (q4 == 0) {
+      s_m[warp][g] = m_run;
+      s_l[warp][g] = l_run;
+    }
+    float* so = s_o + (warp * kMaxG + g) * kD + 32 * q4;  // thread (g, q4) holds row g, dims 32*q4 + 16*e + j
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      so[j] = o[j][0] + c_run;
+      so[16 + j] = o[j][1] + c_run;
+    }
+    // new token logit: fp32 dot of the rotated, un-quantised q and k  (Template.hpp:1410-1441)
+    if (split == 0) {
+      for (int r = warp; r < Gc; r += kWarps) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = fmaf(__half2float(s_q[r * kD + lane * 4 + j]), __half2float(s_k[lane * 4 + j]), acc);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (lane == 0) {
+          s_m[kWarps][r] = acc * sm_scale;
+          s_l[kWarps][r] = 1.f;
+        }
       }
     }
   }
   __syncthreads();
 
-  const int d = threadIdx.x;  // one output dim per thread
-  const int nparts = kWarps + (owner ? 1 : 0);
-  float* part = nullptr;
-  if (nsplit > 1) part = ws_part + ((static_cast<size_t>(b) * num_heads + h0) * nsplit + split) * (kD + 2);
-  for (int r = 0; r < Gc; ++r) {
-    float M = -CUDART_INF_F;
-    for (int w = 0; w < nparts; ++w) M = fmaxf(M, s_m[w][r]);
-    float L = 0.f, acc = 0.f;
-    for (int w = 0; w < kWarps; ++w) {
-      const float e = (s_m[w][r] == -CUDART_INF_F) ? 0.f : exp2f(s_m[w][r] - M);
-      L += s_l[w][r] * e;
-      acc += s_o[w][r][d] * e;
-    }
-    if (owner) {
-      const float e = exp2f(s_m[kWarps][r] - M);
-      L += e;
-      acc += e * __half2float(s_v[d]);
-    }
-    if (nsplit == 1) {
-      // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
-      out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
-    } else {
-      float* pr = part + static_cast<size_t>(r) * nsplit * (kD + 2);
-      pr[d] = acc;
-      if (d == 0) {
-        pr[kD] = M;
-        pr[kD + 1] = L;
+  // ---------------- merge the warps (and the un-quantised new token); one output dim per thread ----------------
+  const bool owner = (split == 0);
+  if (threadIdx.x < kD) {
+    const int d = threadIdx.x;
+    const int nparts = kWarps + (owner ? 1 : 0);
+    float* part = nullptr;
+    if (nsplit > 1) part = ws_part + ((static_cast<size_t>(b) * num_heads + h0) * nsplit + split) * (kD + 2);
+    for (int r = 0; r < Gc; ++r) {
+      float M = -CUDART_INF_F;
+      for (int w = 0; w < nparts; ++w) M = fmaxf(M, s_m[w][r]);
+      float L = 0.f, acc = 0.f;
+      for (int w = 0; w < kWarps; ++w) {
+        const float e = (s_m[w][r] == -CUDART_INF_F) ? 0.f : exp2f(s_m[w][r] - M);
+        L += s_l[w][r] * e;
+        acc += s_o[(w * kMaxG + r) * kD + d] * e;
+      }
+      if (owner) {
+        const float e = exp2f(s_m[kWarps][r] - M);
+        L += e;
+        acc += e * __half2float(s_v[d]);
+      }
+      if (nsplit == 1) {
+        // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
+        out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
+      } else {
+        float* pr = part + static_cast<size_t>(r) * nsplit * (kD + 2);
+        pr[d] = acc;
+        if (d == 0) {
+          pr[kD] = M;
+          pr[kD + 1] = L;
+        }
       }
     }
   }
@@ -486,18 +542,19 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       s_last = last ? 1u : 0u;
     }
     __syncthreads();
-    if (s_last) {
+    if (s_last && threadIdx.x < kD) {
+      const int d = threadIdx.x;
       __threadfence();
       for (int r = 0; r < Gc; ++r) {
         const float* pr = ws_part + (static_cast<size_t>(b) * num_heads + h0 + r) * nsplit * (kD + 2);
         float M = -CUDART_INF_F;
-        for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(pr + s * (kD + 2) + kD));
+        for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(pr + sp * (kD + 2) + kD));
         float L = 0.f, acc = 0.f;
-        for (int s = 0; s < nsplit; ++s) {
-          const float ms = __ldcg(pr + s * (kD + 2) + kD);
+        for (int sp = 0; sp < nsplit; ++sp) {
+          const float ms = __ldcg(pr + sp * (kD + 2) + kD);
           const float e = (ms == -CUDART_INF_F) ? 0.f : exp2f(ms - M);
-          L += __ldcg(pr + s * (kD + 2) + kD + 1) * e;
-          acc += __ldcg(pr + s * (kD + 2) + d) * e;
+          L += __ldcg(pr + sp * (kD + 2) + kD + 1) * e;
+          acc += __ldcg(pr + sp * (kD + 2) + d) * e;
         }
         out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
       }
@@ -612,11 +669,11 @@ __global__ void padding_offsets_kernel(int* __restrict__ out, const int* __restr
 }
 
 template <typename Kern, typename... Args>
-int launch_pdl(Kern kern, dim3 grid, dim3 block, void* stream, const char* what, Args... args) {
+int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, void* stream, const char* what, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -672,13 +729,24 @@ int decode_attention(const DecodeAttnArgs& a) {
     }
   }
   dim3 grid(gx, a.batch, nsplit);
-  auto run = [&](auto kern) {
-    return launch_pdl(kern, grid, dim3(kAttnThreads), a.stream, "single_query_attention", static_cast<const __half*>(a.q),
+  auto run = [&](auto kern, size_t smem) {
+    static bool attr_done[2] = {false, false};
+    const int which = a.int4_kv ? 0 : 1;
+    if (!attr_done[which]) {
+      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "attention smem attribute");
+      if (rc) return rc;
+      attr_done[which] = true;
+    }
+    return launch_pdl(kern, grid, dim3(kAttnThreadsV2), smem, a.stream, "single_query_attention", static_cast<const __half*>(a.q),
                       static_cast<const __half*>(a.k), static_cast<const __half*>(a.v), a.q_stride, a.k_stride, a.v_stride, a.kv_pointers, a.lengths,
                       static_cast<__half*>(a.out), a.num_heads, a.num_kv_heads, a.max_blocks, pg, a.rotary_base, a.rotary_dim, a.timestep, nsplit,
                       part, cnt);
   };
-  return a.int4_kv ? run(decode_attention_kernel<4>) : run(decode_attention_kernel<8>);
+  QS_REQUIRE((a.timestep + 63) / 64 + 1 <= kMaxBlocksSmem, "single_query_attention: context of %d tokens exceeds the %d pages staged in shared memory", a.timestep, kMaxBlocksSmem);
+  QS_REQUIRE(a.tokens_per_block == kPageTokens, "single_query_attention: tokens_per_block=%d, only 64 is supported (cache_engine block_size)", a.tokens_per_block);
+  constexpr size_t kMerge = sizeof(float) * kWarps * kMaxG * kD;
+  const size_t s4 = StageLayout<4>::kBytes * StageLayout<4>::kStages, s8 = StageLayout<8>::kBytes * StageLayout<8>::kStages;
+  return a.int4_kv ? run(decode_attention_kernel<4>, s4 > kMerge ? s4 : kMerge) : run(decode_attention_kernel<8>, s8 > kMerge ? s8 : kMerge);
 }
 
 int prefill_rope_append(const PrefillAppendArgs& a) {
@@ -695,7 +763,7 @@ int prefill_rope_append(const PrefillAppendArgs& a) {
   long long blocks = (work + 3) / 4;
   if (blocks > 148 * 16) blocks = 148 * 16;
   auto run = [&](auto kern) {
-    return launch_pdl(kern, dim3(static_cast<unsigned>(blocks)), dim3(128), a.stream, "apply_bias_rope_update_kv_cache", static_cast<__half*>(a.qkv),
+    return launch_pdl(kern, dim3(static_cast<unsigned>(blocks)), dim3(128), 0, a.stream, "apply_bias_rope_update_kv_cache", static_cast<__half*>(a.qkv),
                       a.seq_lens, a.padding_offset, a.kv_pointers, a.num_tokens, a.max_blocks, a.num_heads, a.num_kv_heads, a.seq_len, pg,
                       a.rotary_base, a.rotary_dim, a.max_positions);
   };
@@ -704,7 +772,7 @@ int prefill_rope_append(const PrefillAppendArgs& a) {
 
 int padding_offsets(int* out, const int* cu_seqlens, int batch, int max_seqlen, void* stream) {
   if (batch == 0) return QS_OK;
-  return launch_pdl(padding_offsets_kernel, dim3(batch), dim3(256), stream, "compute_padding_offsets", out, cu_seqlens, max_seqlen);
+  return launch_pdl(padding_offsets_kernel, dim3(batch), dim3(256), 0, stream, "compute_padding_offsets", out, cu_seqlens, max_seqlen);
 }
 
 }  // namespace qs

@@ -10,7 +10,8 @@ namespace qs {
 
 static thread_local char g_err[1024] = "";
 static int g_pdl = 1;
-static int g_force_upc = 0;
+static int g_force_split = 0;
+static void* g_gemm_prof = nullptr;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -43,12 +44,16 @@ int qs_set_pdl(int enabled) {
   g_pdl = enabled ? 1 : 0;
   return old;
 }
-int qs_gemm_force_units_per_cta(int units) {
-  const int old = g_force_upc;
-  g_force_upc = units;
+int qs_gemm_force_split(int split) {
+  const int old = g_force_split;
+  g_force_split = split;
   return old;
 }
 size_t qs_gemm_workspace_bytes(void) { return gemm_workspace_bytes(); }
+int qs_gemm_set_profile_buffer(void* dev_buffer) {
+  g_gemm_prof = dev_buffer;
+  return 0;
+}
 
 int qs_w4a8_gemm_per_chn(const int8_t* in_feats, const int8_t* kernel, const void* wscales, const void* ascales, const void* w_szs,
                          const void* a_ssums, void* out_feats, int32_t* acc_out, int M, int N, int K, void* workspace, size_t workspace_bytes,
@@ -57,7 +62,7 @@ int qs_w4a8_gemm_per_chn(const int8_t* in_feats, const int8_t* kernel, const voi
   GemmArgs a;
   a.act = in_feats; a.weight = kernel; a.wscales = wscales; a.ascales = ascales; a.w_szs = w_szs; a.a_ssums = a_ssums;
   a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
-  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_units_per_cta = g_force_upc; a.stream = stream;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.prof = g_gemm_prof; a.stream = stream;
   return gemm_w4a8_per_chn(a);
 }
 
@@ -69,7 +74,7 @@ int qs_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
   GemmArgs a;
   a.act = in_feats; a.weight = kernel; a.s2_zeros = zeros; a.s2_scales = scales_i8; a.wscales = wscales; a.ascales = ascales;
   a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
-  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_units_per_cta = g_force_upc; a.stream = stream;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.prof = g_gemm_prof; a.stream = stream;
   return gemm_w4a8_per_group(a);
 }
 
@@ -79,7 +84,7 @@ int qs_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscal
   GemmArgs a;
   a.act = in_feats; a.weight = kernel; a.wscales = wscales; a.ascales = ascales;
   a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
-  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_units_per_cta = g_force_upc; a.stream = stream;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.prof = g_gemm_prof; a.stream = stream;
   return gemm_w8a8(a);
 }
 

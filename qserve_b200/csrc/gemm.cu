@@ -9,16 +9,18 @@
 //     so decode-sized batches (M = 64 tokens) still use full-height 128-row tensor-core instructions.
 //   * the packed INT4 weights are consumed in the checkpoint's own "compute-aware reordered" layout
 //     (w4a8_linear.py:292-322): one 32x32 tile is 512 contiguous bytes, a 32-channel band is contiguous in K.
-//     The TMA engine (cp.async.bulk) stages 4 bands x 2 KB per 128-K block into shared memory; four unpack warps
-//     read one 16-byte lane chunk each (LDS.128), split nibbles in registers (per-group: level-2 dequant
-//     q*s2+z2 with the reference's exact 32-bit multiply + vadd4), and write INT8 rows straight into TENSOR MEMORY
-//     with tcgen05.st.16x128b -- the mma.sync B-fragment order of the checkpoint is exactly the 16x128b TMEM store
+//     ONE TMA tensor copy per 128-K block stages 4 bands x 2 KB into shared memory; four unpack warps read one
+//     16-byte lane chunk each (LDS.128), split nibbles in registers (per-group: level-2 dequant q*s2+z2 with the
+//     reference's exact 32-bit multiply + vadd4), and write INT8 rows straight into TENSOR MEMORY with
+//     tcgen05.st.16x128b -- the mma.sync B-fragment order of the checkpoint is exactly the 16x128b TMEM store
 //     pattern, so no shuffle and no shared-memory round trip is needed.
 //   * one elected thread issues tcgen05.mma.kind::i8 with A (weights) from TMEM and B (INT8 activations, TMA-loaded
 //     with the 128-byte swizzle) from shared memory; INT32 accumulators live in TMEM.
-//   * stream-K style decomposition over (tile, k-block) units so that every SM streams an equal share of the weight
-//     bytes; INT32 partial tiles are exchanged through an L2-resident workspace and summed by the last-arriving CTA
-//     (integer adds: the result is bit-identical for every decomposition).
+//   * decode shapes have too few 128-channel tiles to fill 148 SMs, so K is split across a thread-block CLUSTER
+//     (2/4/8 CTAs); the INT32 partial tiles are reduced through DISTRIBUTED SHARED MEMORY (each CTA sums and finishes
+//     a 1/S slice of the channels) -- integer adds, so the result is bit-identical for every split.
+//   * two CTAs per SM (<= 110 KB smem, 256 TMEM columns each) so one CTA's prologue / epilogue overlaps the other's
+//     weight stream.
 //   * epilogue fused: acc*s1[n]*sa[m] - s1z[n]*asum[m] (per-channel) or acc*(s1[n]*sa[m]) (per-group, W8A8) -> fp16.
 //   * programmatic dependent launch: the weight prefetch is issued before griddepcontrol.wait, so HBM keeps streaming
 //     while the preceding activation-quant kernel drains.
@@ -40,7 +42,6 @@ constexpr int kEpiThreads = 128;
 enum { kModeW4Chn = 0, kModeW4Grp = 1, kModeW8 = 2 };
 
 struct GemmParams {
-  const uint8_t* qweight;    // W4: packed [N, K/2]; W8: unused (tensor map)
   const uint8_t* s2_scales;  // per-group: [K/128, N] (shuffled per 32 columns, as stored in the checkpoint)
   const uint8_t* s2_zeros;   // per-group: [K/128, N]
   const __half* wscales;     // [N]
@@ -49,10 +50,9 @@ struct GemmParams {
   const __half* a_ssums;     // [M]  (per-channel only)
   __half* out;               // [M, N]
   int32_t* acc_out;          // optional: raw INT32 accumulators [M, N] (parity tests)
-  int32_t* ws_partials;
-  uint32_t* ws_counters;
   int M, N, K;
-  int m_tiles, kb_per_tile, total_units, units_per_cta, max_contrib;
+  int m_tiles, kb_per_tile, split;
+  unsigned long long* prof;  // optional: 16 globaltimer stamps per CTA (tools/gemm_timeline.py)
 };
 
 template <int MODE, int NT, int STAGES>
@@ -69,14 +69,42 @@ struct Cfg {
   static constexpr int kOffAct = 0;
   static constexpr int kOffW = kOffAct + STAGES * kActBytes;
   static constexpr int kOffS2 = kOffW + STAGES * kWBytes;
-  static constexpr int kOffRow = kOffS2 + STAGES * kS2Bytes;  // float ascales[NT], asums[NT]
+  static constexpr int kPipeBytes = kOffS2 + STAGES * kS2Bytes;
+  static constexpr int kRedBytes = NT * kBM * 4;  // INT32 partial tile [NT][128], aliases the pipeline buffers
+  static constexpr int kOffRow = (kPipeBytes > kRedBytes ? kPipeBytes : kRedBytes);  // float ascales[NT], asums[NT]
   static constexpr int kOffBar = kOffRow + 2 * NT * 4;
-  static constexpr int kNumBars = 3 * STAGES + 2;
-  static constexpr int kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr, flag
+  static constexpr int kNumBars = 3 * STAGES + 1;
+  static constexpr int kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr
   static constexpr int kSmemBytes = kOffMisc + 16 + 1024;  // + alignment slack
+  // two co-resident CTAs per SM when both the TMEM columns (<= 256 each) and the shared memory (<= 113 KB each) allow it
+  static constexpr int kCtasPerSm = (kTmemCols <= 256 && kSmemBytes <= 113 * 1024) ? 2 : 1;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+  return t;
+}
+#define QS_PROF(slot) do { if (p.prof) p.prof[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ int2 ld_dsmem_v2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared::cluster.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
 
 template <int MODE>
 __device__ __forceinline__ __half epilogue_one(int32_t acc, float ws, float wsz, float as, float asum) {
@@ -93,8 +121,9 @@ __device__ __forceinline__ __half epilogue_one(int32_t acc, float ws, float wsz,
   }
 }
 
+// grid.x = tiles * split; the `split` CTAs of a cluster share one (n_tile, m_tile) and own disjoint K ranges
 template <int MODE, int NT, int STAGES>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, Cfg<MODE, NT, STAGES>::kCtasPerSm)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   using C = Cfg<MODE, NT, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -102,33 +131,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   uint8_t* s_act = smem + C::kOffAct;
   uint8_t* s_w = smem + C::kOffW;
   uint8_t* s_s2 = smem + C::kOffS2;
+  int32_t* s_red = reinterpret_cast<int32_t*>(smem);  // aliases the pipeline buffers once the mainloop has drained
   float* s_asc = reinterpret_cast<float*>(smem + C::kOffRow);
   float* s_asum = s_asc + NT;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* bar_afull = bar_full + STAGES;
   uint64_t* bar_empty = bar_afull + STAGES;
   uint64_t* bar_dfull = bar_empty + STAGES;
-  uint64_t* bar_dempty = bar_dfull + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kOffMisc);
-  volatile uint32_t* s_flag = s_tmem + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int S = p.split;
+  const int rank = (S > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int tile = blockIdx.x / S;
+  const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+  // balanced K split: rank r owns k-blocks [kb_begin, kb_end)
   const int KB = p.kb_per_tile;
-
-  const int unit_begin = blockIdx.x * p.units_per_cta;
-  const int unit_end = min(unit_begin + p.units_per_cta, p.total_units);
+  const int kb_begin = (KB * rank) / S, kb_end = (KB * (rank + 1)) / S;
+  const int n_kb = kb_end - kb_begin;
+  if (threadIdx.x == 0) QS_PROF(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_act);
-    if (MODE == kModeW8) tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_w);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_afull[i], 4);
       mbar_init(&bar_empty[i], 1);
     }
     mbar_init(bar_dfull, 1);
-    mbar_init(bar_dempty, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::kTmemCols>(s_tmem);
@@ -136,231 +168,196 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (threadIdx.x == 0) pdl_launch_dependents();
+  if (threadIdx.x == 0) { pdl_launch_dependents(); QS_PROF(1); }
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer (one elected lane issues) =====================================
     if (lane == 0) {
-      const uint64_t pol_w = policy_evict_first();  // weights are streamed once per step
-      auto issue_weights = [&](int u, int it) {
-        const int s = it % STAGES;
-        const int tile = u / KB, kb = u - tile * KB;
-        const int n_tile = tile / p.m_tiles;
-        if (it >= STAGES) mbar_wait(&bar_empty[s], ((it / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&bar_full[s], C::kStageTx);
-        if constexpr (MODE == kModeW8) {
-          tma_load_2d(s_w + s * C::kWBytes, &tmap_w, kb * kBK, n_tile * kBM, &bar_full[s]);
-        } else {
-          // band b of the tile: 4 consecutive 32x32 tiles (2 KB) at ((n32 * K/32) + k32) * 512
-          const size_t k32 = static_cast<size_t>(kb) * 4;
-          const size_t tiles_per_band = static_cast<size_t>(p.K) / 32;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const size_t n32 = static_cast<size_t>(n_tile) * 4 + b;
-            bulk_copy_g2s_hint(s_w + s * C::kWBytes + b * 2048, p.qweight + (n32 * tiles_per_band + k32) * 512, 2048,
-                               &bar_full[s], pol_w);
-          }
-          if constexpr (MODE == kModeW4Grp) {
-            const size_t off = static_cast<size_t>(kb) * p.N + static_cast<size_t>(n_tile) * kBM;
-            bulk_copy_g2s(s_s2 + s * C::kS2Bytes, p.s2_scales + off, kBM, &bar_full[s]);
-            bulk_copy_g2s(s_s2 + s * C::kS2Bytes + kBM, p.s2_zeros + off, kBM, &bar_full[s]);
-          }
-        }
-      };
-      auto issue_act = [&](int u, int it) {
-        const int s = it % STAGES;
-        const int tile = u / KB, kb = u - tile * KB;
-        const int m_tile = tile % p.m_tiles;
-        tma_load_2d(s_act + s * C::kActBytes, &tmap_act, kb * kBK, m_tile * NT, &bar_full[s]);
-      };
+      const int w_row = (MODE == kModeW8) ? n_tile * kBM : n_tile * 4;  // W8: row of [N,K]; W4: band index
+      const int a_row = m_tile * NT;
+      const uint8_t* s2s = p.s2_scales + static_cast<size_t>(n_tile) * kBM;
+      const uint8_t* s2z = p.s2_zeros + static_cast<size_t>(n_tile) * kBM;
       // static weights do not depend on the previous kernel: prefetch a full ring before the PDL wait
-      const int n_units = unit_end - unit_begin;
-      const int pre = n_units < STAGES ? n_units : STAGES;
-      for (int it = 0; it < pre; ++it) issue_weights(unit_begin + it, it);
-      pdl_wait();
-      for (int it = 0; it < pre; ++it) issue_act(unit_begin + it, it);
-      for (int it = pre; it < n_units; ++it) {
-        issue_weights(unit_begin + it, it);
-        issue_act(unit_begin + it, it);
+      const int pre = n_kb < STAGES ? n_kb : STAGES;
+      for (int it = 0; it < pre; ++it) {
+        const int kb = kb_begin + it;
+        mbar_expect_tx(&bar_full[it], C::kStageTx);
+        // W4: u64 elements, 256 per 128-K block of one band (4 tiles x 512 B); W8: bytes
+        tma_load_2d(s_w + it * C::kWBytes, &tmap_w, (MODE == kModeW8) ? kb * kBK : kb * 256, w_row, &bar_full[it]);
+        if constexpr (MODE == kModeW4Grp) {
+          bulk_copy_g2s(s_s2 + it * C::kS2Bytes, s2s + static_cast<size_t>(kb) * p.N, kBM, &bar_full[it]);
+          bulk_copy_g2s(s_s2 + it * C::kS2Bytes + kBM, s2z + static_cast<size_t>(kb) * p.N, kBM, &bar_full[it]);
+        }
       }
+      pdl_wait();
+      QS_PROF(2);
+      for (int it = 0; it < pre; ++it) tma_load_2d(s_act + it * C::kActBytes, &tmap_act, (kb_begin + it) * kBK, a_row, &bar_full[it]);
+      int s = 0;
+      uint32_t ph = 0;  // parity of the (it / STAGES - 1)-th completion of empty[s]
+      for (int it = pre; it < n_kb; ++it) {
+        const int kb = kb_begin + it;
+        mbar_wait(&bar_empty[s], ph);
+        mbar_expect_tx(&bar_full[s], C::kStageTx);
+        tma_load_2d(s_w + s * C::kWBytes, &tmap_w, (MODE == kModeW8) ? kb * kBK : kb * 256, w_row, &bar_full[s]);
+        if constexpr (MODE == kModeW4Grp) {
+          bulk_copy_g2s(s_s2 + s * C::kS2Bytes, s2s + static_cast<size_t>(kb) * p.N, kBM, &bar_full[s]);
+          bulk_copy_g2s(s_s2 + s * C::kS2Bytes + kBM, s2z + static_cast<size_t>(kb) * p.N, kBM, &bar_full[s]);
+        }
+        tma_load_2d(s_act + s * C::kActBytes, &tmap_act, kb * kBK, a_row, &bar_full[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      QS_PROF(3);
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_i8(kBM, NT, 1u, 1u);
-      int it = 0, seg = 0;
-      for (int u = unit_begin; u < unit_end; ++seg) {
-        const int tile = u / KB, kb0 = u - tile * KB;
-        const int kb1 = min(KB, kb0 + (unit_end - u));
-        if (seg > 0) {
-          mbar_wait(bar_dempty, (seg - 1) & 1);  // epilogue has drained the accumulator of the previous segment
-          tc_fence_after();
-        }
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&bar_full[s], ph);
-          if constexpr (MODE != kModeW8) mbar_wait(&bar_afull[s], ph);
-          tc_fence_after();
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + s * C::kActBytes));
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_kb; ++it) {
+        mbar_wait(&bar_full[s], ph);
+        if (it == 0) QS_PROF(4);
+        if constexpr (MODE != kModeW8) mbar_wait(&bar_afull[s], ph);
+        tc_fence_after();
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + s * C::kActBytes));
 #pragma unroll
-          for (int t = 0; t < kBK / 32; ++t) {
-            const uint32_t acc = (kb > kb0 || t > 0) ? 1u : 0u;
-            if constexpr (MODE == kModeW8) {
-              const uint64_t adesc = umma_desc_sw128(smem_u32(s_w + s * C::kWBytes));
-              umma_i8_ss(tmem_base, adesc + t * 2, bdesc + t * 2, idesc, acc);
-            } else {
-              umma_i8_ts(tmem_base, tmem_base + NT + s * (kBK / 4) + t * 8, bdesc + t * 2, idesc, acc);
-            }
+        for (int t = 0; t < kBK / 32; ++t) {
+          const uint32_t acc = (it > 0 || t > 0) ? 1u : 0u;
+          if constexpr (MODE == kModeW8) {
+            const uint64_t adesc = umma_desc_sw128(smem_u32(s_w + s * C::kWBytes));
+            umma_i8_ss(tmem_base, adesc + t * 2, bdesc + t * 2, idesc, acc);
+          } else {
+            umma_i8_ts(tmem_base, tmem_base + NT + s * (kBK / 4) + t * 8, bdesc + t * 2, idesc, acc);
           }
-          umma_commit(&bar_empty[s]);
         }
-        umma_commit(bar_dfull);
-        u += kb1 - kb0;
+        umma_commit(&bar_empty[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      umma_commit(bar_dfull);
+      QS_PROF(6);
     }
   } else {
     // ===================================== unpack + epilogue warps =====================================
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int epi_tid = quad * 32 + lane; // 0..127 == channel row inside the tile
-    int it = 0, seg = 0;
-    bool waited = false;
-    for (int u = unit_begin; u < unit_end; ++seg) {
-      const int tile = u / KB, kb0 = u - tile * KB;
-      const int kb1 = min(KB, kb0 + (unit_end - u));
-      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-
-      if constexpr (MODE != kModeW8) {
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&bar_full[s], (it / STAGES) & 1);
-          const uint8_t* wsrc = s_w + s * C::kWBytes + quad * 2048 + lane * 16;
-          const uint32_t tdst = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + NT + s * (kBK / 4);
-          uint32_t sc4 = 0, zp4 = 0;
+    if constexpr (MODE != kModeW8) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_kb; ++it) {
+        mbar_wait(&bar_full[s], ph);
+        const uint8_t* wsrc = s_w + s * C::kWBytes + quad * 2048 + lane * 16;
+        const uint32_t tdst = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + NT + s * (kBK / 4);
+        uint32_t sc4 = 0, zp4 = 0;
+        if constexpr (MODE == kModeW4Grp) {
+          const uint8_t* s2 = s_s2 + s * C::kS2Bytes + quad * 32 + (lane >> 2) * 4;
+          sc4 = *reinterpret_cast<const uint32_t*>(s2);
+          zp4 = *reinterpret_cast<const uint32_t*>(s2 + kBM);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint4 v = *reinterpret_cast<const uint4*>(wsrc + t * 512);
+          uint32_t xl = v.x & 0x0F0F0F0Fu, xh = (v.x >> 4) & 0x0F0F0F0Fu;
+          uint32_t yl = v.y & 0x0F0F0F0Fu, yh = (v.y >> 4) & 0x0F0F0F0Fu;
+          uint32_t zl = v.z & 0x0F0F0F0Fu, zh = (v.z >> 4) & 0x0F0F0F0Fu;
+          uint32_t wl = v.w & 0x0F0F0F0Fu, wh = (v.w >> 4) & 0x0F0F0F0Fu;
           if constexpr (MODE == kModeW4Grp) {
-            const uint8_t* s2 = s_s2 + s * C::kS2Bytes + quad * 32 + (lane >> 2) * 4;
-            sc4 = *reinterpret_cast<const uint32_t*>(s2);
-            zp4 = *reinterpret_cast<const uint32_t*>(s2 + kBM);
+            // w4a8_per_group/gemm_cuda.cu:298-324: 32-bit multiply of four nibble-bytes, then vadd4 with the s8 zero
+            const uint32_t s0 = sc4 & 0xFF, s1 = (sc4 >> 8) & 0xFF, s2 = (sc4 >> 16) & 0xFF, s3 = sc4 >> 24;
+            const uint32_t z0 = __byte_perm(zp4, 0, 0x0000), z1 = __byte_perm(zp4, 0, 0x1111);
+            const uint32_t z2 = __byte_perm(zp4, 0, 0x2222), z3 = __byte_perm(zp4, 0, 0x3333);
+            xl = __vadd4(xl * s0, z0); zl = __vadd4(zl * s0, z0);   // channel c
+            yl = __vadd4(yl * s1, z1); wl = __vadd4(wl * s1, z1);   // channel c + 8
+            xh = __vadd4(xh * s2, z2); zh = __vadd4(zh * s2, z2);   // channel c + 16
+            yh = __vadd4(yh * s3, z3); wh = __vadd4(wh * s3, z3);   // channel c + 24
           }
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const uint4 v = *reinterpret_cast<const uint4*>(wsrc + t * 512);
-            uint32_t xl = v.x & 0x0F0F0F0Fu, xh = (v.x >> 4) & 0x0F0F0F0Fu;
-            uint32_t yl = v.y & 0x0F0F0F0Fu, yh = (v.y >> 4) & 0x0F0F0F0Fu;
-            uint32_t zl = v.z & 0x0F0F0F0Fu, zh = (v.z >> 4) & 0x0F0F0F0Fu;
-            uint32_t wl = v.w & 0x0F0F0F0Fu, wh = (v.w >> 4) & 0x0F0F0F0Fu;
-            if constexpr (MODE == kModeW4Grp) {
-              // w4a8_per_group/gemm_cuda.cu:298-324: 32-bit multiply of four nibble-bytes, then vadd4 with the s8 zero
-              const uint32_t s0 = sc4 & 0xFF, s1 = (sc4 >> 8) & 0xFF, s2 = (sc4 >> 16) & 0xFF, s3 = sc4 >> 24;
-              const uint32_t z0 = __byte_perm(zp4, 0, 0x0000), z1 = __byte_perm(zp4, 0, 0x1111);
-              const uint32_t z2 = __byte_perm(zp4, 0, 0x2222), z3 = __byte_perm(zp4, 0, 0x3333);
-              xl = __vadd4(xl * s0, z0); zl = __vadd4(zl * s0, z0);   // channel c
-              yl = __vadd4(yl * s1, z1); wl = __vadd4(wl * s1, z1);   // channel c + 8
-              xh = __vadd4(xh * s2, z2); zh = __vadd4(zh * s2, z2);   // channel c + 16
-              yh = __vadd4(yh * s3, z3); wh = __vadd4(wh * s3, z3);   // channel c + 24
-            }
-            // lanes 0..15 of the quadrant <- channels c, c+8 ; lanes 16..31 <- channels c+16, c+24 ; 8 columns = 32 k
-            tmem_st_16x128b_x2(tdst + t * 8, xl, yl, zl, wl);
-            tmem_st_16x128b_x2(tdst + t * 8 + (16u << 16), xh, yh, zh, wh);
-          }
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_afull[s]);
+          // lanes 0..15 of the quadrant <- channels c, c+8 ; lanes 16..31 <- channels c+16, c+24 ; 8 columns = 32 k
+          tmem_st_16x128b_x2(tdst + t * 8, xl, yl, zl, wl);
+          tmem_st_16x128b_x2(tdst + t * 8 + (16u << 16), xh, yh, zh, wh);
         }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_afull[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-
-      // ------------------------------- epilogue of this segment -------------------------------
-      if (!waited) {
-        pdl_wait();  // ascales / a_ssums / out / workspace belong to the dependency chain
-        waited = true;
-      }
-      const int m0 = m_tile * NT;
-      const int n = n_tile * kBM + epi_tid;
-      // stage the per-token scales of this token tile
-      for (int j = epi_tid; j < NT; j += kEpiThreads) {
-        const bool ok = (m0 + j) < p.M;
-        s_asc[j] = ok ? __half2float(p.ascales[m0 + j]) : 0.f;
-        if constexpr (MODE == kModeW4Chn) s_asum[j] = ok ? __half2float(p.a_ssums[m0 + j]) : 0.f;
-      }
-      const float ws = __half2float(p.wscales[n]);
-      float wsz = 0.f;
-      if constexpr (MODE == kModeW4Chn) wsz = __half2float(p.w_szs[n]);
-
-      mbar_wait(bar_dfull, seg & 1);
-      tc_fence_after();
-      epi_bar_sync();  // s_asc / s_asum visible
-
-      const bool full_k = (kb0 == 0 && kb1 == KB);
-      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-      int ncontrib = 1, first_cta = 0;
-      if (!full_k) {
-        first_cta = (tile * KB) / p.units_per_cta;
-        const int last_cta = ((tile + 1) * KB - 1) / p.units_per_cta;
-        ncontrib = last_cta - first_cta + 1;
-        int32_t* slot = p.ws_partials + (static_cast<size_t>(tile) * p.max_contrib + (blockIdx.x - first_cta)) * (NT * kBM);
-#pragma unroll 1
-        for (int c = 0; c < NT / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(trow + c * 32, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) __stcg(slot + (c * 32 + i) * kBM + epi_tid, static_cast<int32_t>(r[i]));
-        }
-      }
-      bool do_final = full_k;
-      if (!full_k) {
-        __threadfence();
-        epi_bar_sync();
-        if (epi_tid == 0) {
-          const uint32_t old = atomicAdd(&p.ws_counters[tile], 1u);
-          const bool last = (old == static_cast<uint32_t>(ncontrib - 1));
-          if (last) p.ws_counters[tile] = 0;  // self-cleaning for the next launch
-          *s_flag = last ? 1u : 0u;
-        }
-        epi_bar_sync();
-        do_final = (*s_flag != 0);
-        if (do_final) __threadfence();
-      }
-      if (do_final) {
-        const int32_t* slot0 = p.ws_partials + static_cast<size_t>(tile) * p.max_contrib * (NT * kBM);
-#pragma unroll 1
-        for (int c = 0; c < NT / 32; ++c) {
-          uint32_t r[32];
-          if (full_k) {
-            tmem_ld_32x32b_x32(trow + c * 32, r);
-            tmem_wait_ld();
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = 0;
-            for (int j = 0; j < ncontrib; ++j) {
-              const int32_t* sl = slot0 + static_cast<size_t>(j) * (NT * kBM);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] += static_cast<uint32_t>(__ldcg(sl + (c * 32 + i) * kBM + epi_tid));
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int m = m0 + c * 32 + i;
-            if (m < p.M) {
-              const int32_t acc = static_cast<int32_t>(r[i]);
-              p.out[static_cast<size_t>(m) * p.N + n] = epilogue_one<MODE>(acc, ws, wsz, s_asc[c * 32 + i], s_asum[c * 32 + i]);
-              if (p.acc_out) p.acc_out[static_cast<size_t>(m) * p.N + n] = acc;
-            }
-          }
-        }
-      }
-      // accumulator drained: release it to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dempty);
-      epi_bar_sync();  // s_asc/s_asum/s_flag reuse across segments
-      u += kb1 - kb0;
     }
+
+    // ------------------------------------------ epilogue ------------------------------------------
+    pdl_wait();  // ascales / a_ssums / out belong to the dependency chain
+    const int m0 = m_tile * NT;
+    for (int j = epi_tid; j < NT; j += kEpiThreads) {
+      const bool ok = (m0 + j) < p.M;
+      s_asc[j] = ok ? __half2float(p.ascales[m0 + j]) : 0.f;
+      if constexpr (MODE == kModeW4Chn) s_asum[j] = ok ? __half2float(p.a_ssums[m0 + j]) : 0.f;
+    }
+    if (epi_tid == 0) QS_PROF(7);
+    mbar_wait(bar_dfull, 0);   // all MMAs retired: accumulators complete, pipeline buffers free
+    tc_fence_after();
+    if (epi_tid == 0) QS_PROF(8);
+    // TMEM -> shared memory, transposed to [token][channel] so that channel pairs are contiguous
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < NT / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(trow + c * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s_red[(c * 32 + i) * kBM + epi_tid] = static_cast<int32_t>(r[i]);
+    }
+    if (epi_tid == 0) QS_PROF(9);
   }
 
+  // ---------------- cross-CTA (cluster) reduction of the INT32 partial tiles through distributed shared memory ----------------
   tc_fence_before();
-  __syncthreads();
+  if (S > 1) cluster_sync_all(); else __syncthreads();
+  if (warp >= 2) {
+    const int epi_tid = (warp & 3) * 32 + lane;
+    if (epi_tid == 0) QS_PROF(10);
+    // this CTA finishes channel pairs [pair0, pair1) of the tile for all NT tokens
+    const int pair0 = (64 * rank) / S, pair1 = (64 * (rank + 1)) / S;
+    const int npairs = pair1 - pair0;
+    const int m0 = m_tile * NT;
+    const uint32_t red_local = smem_u32(s_red);
+    uint32_t red_peer[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) red_peer[r] = (S > 1 && r < S) ? map_to_cta(red_local, r) : red_local;
+    for (int idx = epi_tid; idx < npairs * NT; idx += kEpiThreads) {
+      const int pr = pair0 + idx % npairs, tok = idx / npairs;
+      const int m = m0 + tok;
+      const uint32_t off = static_cast<uint32_t>((tok * kBM + 2 * pr) * 4);
+      int2 acc = make_int2(0, 0);
+      if (S == 1) {
+        acc = *reinterpret_cast<const int2*>(reinterpret_cast<const uint8_t*>(s_red) + off);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r < S) {
+            const int2 v = ld_dsmem_v2(red_peer[r] + off);
+            acc.x += v.x;
+            acc.y += v.y;
+          }
+        }
+      }
+      if (m < p.M) {
+        const int n = n_tile * kBM + 2 * pr;
+        const __half2 ws = *reinterpret_cast<const __half2*>(p.wscales + n);
+        float wz0 = 0.f, wz1 = 0.f;
+        if constexpr (MODE == kModeW4Chn) {
+          const __half2 wz = *reinterpret_cast<const __half2*>(p.w_szs + n);
+          wz0 = __low2float(wz); wz1 = __high2float(wz);
+        }
+        const float as = s_asc[tok], asum = s_asum[tok];
+        const __half o0 = epilogue_one<MODE>(acc.x, __low2float(ws), wz0, as, asum);
+        const __half o1 = epilogue_one<MODE>(acc.y, __high2float(ws), wz1, as, asum);
+        *reinterpret_cast<__half2*>(p.out + static_cast<size_t>(m) * p.N + n) = __halves2half2(o0, o1);
+        if (p.acc_out) *reinterpret_cast<int2*>(p.acc_out + static_cast<size_t>(m) * p.N + n) = acc;
+      }
+    }
+    if (epi_tid == 0) QS_PROF(11);
+  }
+  // no CTA may exit (and free its shared memory) while peers are still reading it
+  if (S > 1) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) QS_PROF(12);
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
@@ -397,6 +394,21 @@ int make_tmap_u8(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
   return QS_OK;
 }
 
+// packed INT4 weights [N, K/2] seen as [N/32 bands][K*16 bytes] of uint64 elements; box = 4 bands x 2 KB (one 128-K block)
+int make_tmap_w4(CUtensorMap* m, const void* ptr, uint64_t N, uint64_t K) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(QS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {K * 16 / 8, N / 32};
+  cuuint64_t strides[1] = {K * 16};
+  cuuint32_t box[2] = {256, 4};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_INT64, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(QS_ERR_CUDA, "cuTensorMapEncodeTiled(w4) failed (%d): ptr=%p N=%llu K=%llu", (int)r, ptr, (unsigned long long)N,
+                                          (unsigned long long)K);
+  return QS_OK;
+}
+
 int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {
@@ -408,13 +420,24 @@ int num_sms() {
   return g_num_sms;
 }
 
-constexpr size_t kCounterBytes = 64 * 1024;  // 16384 tile counters
+int choose_split(int tiles, int kb_per_tile, int forced) {
+  int s = 1;
+  if (forced > 0) {
+    s = forced;
+  } else {
+    const int sms = num_sms();
+    // smallest power of two that brings the CTA count to >= ~2/3 of the SMs; every CTA keeps >= 2 k-blocks
+    while (s < 8 && tiles * s < (2 * sms) / 3 && kb_per_tile / (2 * s) >= 2) s *= 2;
+  }
+  if (s > 8) s = 8;
+  while (s > 1 && kb_per_tile < s) s /= 2;
+  return s;
+}
 
 template <int MODE, int NT, int STAGES>
 int launch_gemm(const GemmArgs& a) {
   using C = Cfg<MODE, NT, STAGES>;
   GemmParams p{};
-  p.qweight = static_cast<const uint8_t*>(a.weight);
   p.s2_scales = static_cast<const uint8_t*>(a.s2_scales);
   p.s2_zeros = static_cast<const uint8_t*>(a.s2_zeros);
   p.wscales = static_cast<const __half*>(a.wscales);
@@ -423,54 +446,19 @@ int launch_gemm(const GemmArgs& a) {
   p.a_ssums = static_cast<const __half*>(a.a_ssums);
   p.out = static_cast<__half*>(a.out);
   p.acc_out = static_cast<int32_t*>(a.acc_out);
+  p.prof = static_cast<unsigned long long*>(a.prof);
   p.M = a.M; p.N = a.N; p.K = a.K;
   const int n_tiles = a.N / kBM;
   p.m_tiles = (a.M + NT - 1) / NT;
   p.kb_per_tile = a.K / kBK;
   const int tiles = n_tiles * p.m_tiles;
-  p.total_units = tiles * p.kb_per_tile;
-
-  // ---- decomposition: equal shares of k-blocks per CTA (stream-K) when the tile count does not fill the machine ----
-  const int sms = num_sms();
-  int upc = p.kb_per_tile;  // default: one whole tile per CTA
-  int max_contrib = 1;
-  const size_t slot_bytes = static_cast<size_t>(NT) * kBM * 4;
-  if (a.force_units_per_cta > 0) {
-    upc = a.force_units_per_cta;
-  } else if (tiles < 4 * sms) {
-    const int target = (tiles <= sms) ? sms : ((tiles + sms - 1) / sms) * sms;  // CTAs
-    upc = (p.total_units + target - 1) / target;
-    if (upc < 2) upc = 2;  // keep at least two k-blocks per CTA
-    if (upc > p.kb_per_tile) upc = ((upc + p.kb_per_tile - 1) / p.kb_per_tile) * p.kb_per_tile;
-  } else {
-    // plenty of tiles: whole tiles, several per CTA, persistent-style
-    const int per = (tiles + 2 * sms - 1) / (2 * sms);
-    upc = per * p.kb_per_tile;
-  }
-  if (upc % p.kb_per_tile != 0) {
-    max_contrib = (p.kb_per_tile + upc - 1) / upc + 1;
-    const size_t need = kCounterBytes + static_cast<size_t>(tiles) * max_contrib * slot_bytes;
-    if (tiles > static_cast<int>(kCounterBytes / 4) || a.workspace == nullptr || need > a.workspace_bytes) {
-      if (a.force_units_per_cta > 0) return set_error(QS_ERR_WORKSPACE, "gemm workspace too small: need %zu have %zu", need, a.workspace_bytes);
-      upc = p.kb_per_tile;  // fall back to whole tiles (no exchange)
-      max_contrib = 1;
-    }
-  }
-  p.units_per_cta = upc;
-  p.max_contrib = max_contrib;
-  p.ws_counters = static_cast<uint32_t*>(a.workspace);
-  p.ws_partials = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(a.workspace) + kCounterBytes);
-  const int grid = (p.total_units + upc - 1) / upc;
+  p.split = choose_split(tiles, p.kb_per_tile, a.force_split);
 
   CUtensorMap tm_act, tm_w;
   int rc = make_tmap_u8(&tm_act, a.act, a.M, a.K, NT);
   if (rc) return rc;
-  if (MODE == kModeW8) {
-    rc = make_tmap_u8(&tm_w, a.weight, a.N, a.K, kBM);
-    if (rc) return rc;
-  } else {
-    tm_w = tm_act;
-  }
+  rc = (MODE == kModeW8) ? make_tmap_u8(&tm_w, a.weight, a.N, a.K, kBM) : make_tmap_w4(&tm_w, a.weight, a.N, a.K);
+  if (rc) return rc;
 
   auto kern = gemm_kernel<MODE, NT, STAGES>;
   static bool attr_set = false;
@@ -480,15 +468,19 @@ int launch_gemm(const GemmArgs& a) {
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
+  cfg.gridDim = dim3(tiles * p.split);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = static_cast<cudaStream_t>(a.stream);
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = p.split;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, tm_act, tm_w, p), "gemm launch");
 }
 
@@ -498,9 +490,10 @@ int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.N % kBM == 0, "gemm: N=%d must be a multiple of %d", a.N, kBM);
   QS_REQUIRE(a.K % kBK == 0, "gemm: K=%d must be a multiple of %d", a.K, kBK);
   QS_REQUIRE((reinterpret_cast<uintptr_t>(a.act) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.weight) & 15) == 0, "gemm: operands must be 16-byte aligned");
-  if (a.M <= 32) return launch_gemm<MODE, 32, 8>(a);
-  if (a.M <= 64) return launch_gemm<MODE, 64, 8>(a);
-  if (a.M <= 128) return launch_gemm<MODE, 128, (MODE == kModeW8 ? 6 : 8)>(a);
+  QS_REQUIRE(a.force_split == 0 || a.force_split == 1 || a.force_split == 2 || a.force_split == 4 || a.force_split == 8, "gemm: split must be 1, 2, 4 or 8");
+  if (a.M <= 32) return launch_gemm<MODE, 32, (MODE == kModeW8 ? 4 : 6)>(a);
+  if (a.M <= 64) return launch_gemm<MODE, 64, (MODE == kModeW8 ? 4 : 6)>(a);
+  if (a.M <= 128) return launch_gemm<MODE, 128, (MODE == kModeW8 ? 3 : 4)>(a);
   return launch_gemm<MODE, 256, (MODE == kModeW8 ? 4 : 5)>(a);
 }
 
@@ -509,6 +502,6 @@ int dispatch_gemm(const GemmArgs& a) {
 int gemm_w4a8_per_chn(const GemmArgs& a) { return dispatch_gemm<kModeW4Chn>(a); }
 int gemm_w4a8_per_group(const GemmArgs& a) { return dispatch_gemm<kModeW4Grp>(a); }
 int gemm_w8a8(const GemmArgs& a) { return dispatch_gemm<kModeW8>(a); }
-size_t gemm_workspace_bytes() { return kCounterBytes + static_cast<size_t>(96) * 1024 * 1024; }
+size_t gemm_workspace_bytes() { return 4096; }  // the cluster/DSMEM split-K needs no global workspace; kept for ABI stability
 
 }  // namespace qs

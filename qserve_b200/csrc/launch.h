@@ -21,7 +21,8 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0;
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
-  int force_units_per_cta = 0;  // tests: force a stream-K decomposition
+  int force_split = 0;          // tests: force the cluster split-K factor (1, 2, 4, 8); 0 = automatic
+  void* prof = nullptr;         // optional device buffer: 16 x uint64 globaltimer stamps per CTA
   void* stream = nullptr;
 };
 

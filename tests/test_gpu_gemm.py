@@ -88,28 +88,41 @@ def test_w8a8(dev, M, N, K):
     assert np.array_equal(bits16(np_of(out)), bits16(out_o)), info
 
 
-@pytest.mark.parametrize("upc", [1, 3, 5, 8, 32])
-def test_stream_k_decompositions_are_bit_identical(dev, upc):
-    """INT32 partial tiles exchanged through the workspace: every decomposition gives the same bits."""
-    import qserve_backend.qgemm_w4a8_per_chn as op
+@pytest.mark.parametrize("split", [1, 2, 4, 8])
+@pytest.mark.parametrize("mode", ["chn", "grp", "w8"])
+def test_cluster_split_k_is_bit_identical(dev, split, mode):
+    """INT32 partial tiles reduced through distributed shared memory: every split factor gives the same bits."""
     from qserve_b200._lib import lib
+    import qserve_backend.qgemm_w4a8_per_chn as opc
+    import qserve_backend.qgemm_w4a8_per_group as opg
+    import qserve_backend.qgemm_w8a8 as op8
     M, N, K = 64, 512, 2048
     rng = np.random.default_rng(99)
-    q, qw, s1, s1z = w4a8.synth_per_channel(rng, N, K)
     aq, sa, asum = _acts(rng, M, K)
-    out_o, acc_o = w4a8.gemm_w4a8_per_chn(aq, qw, s1, sa, s1z, asum, return_acc=True)
-    args = [to_dev(a, dev) for a in (aq, qw, s1, sa, s1z, asum)]
-    lib.qs_gemm_force_units_per_cta(upc)
+    if mode == "chn":
+        q, qw, s1, s1z = w4a8.synth_per_channel(rng, N, K)
+        out_o, acc_o = w4a8.gemm_w4a8_per_chn(aq, qw, s1, sa, s1z, asum, return_acc=True)
+        call = lambda out, acc: opc.gemm_forward_cuda(*[to_dev(a, dev) for a in (aq, qw, s1, sa, s1z, asum)], out, _acc_out=acc)
+    elif mode == "grp":
+        q, qw, s1, s2s, s2z = w4a8.synth_per_group(rng, N, K)
+        out_o, acc_o = w4a8.gemm_w4a8_per_group(aq, qw, s2z, s2s, s1, sa, return_acc=True)
+        call = lambda out, acc: opg.gemm_forward_cuda(*[to_dev(a, dev) for a in (aq, qw, s2z, s2s, s1, sa)], out, _acc_out=acc)
+    else:
+        w = rng.integers(-128, 128, size=(N, K), dtype=np.int8)
+        sw = rng.uniform(0.001, 0.01, size=N).astype(np.float16)
+        out_o, acc_o = w4a8.gemm_w8a8(aq, w, sw, sa, return_acc=True)
+        call = lambda out, acc: op8.w8a8_gemm_forward_cuda(*[to_dev(a, dev) for a in (aq, w, sw, sa)], out, _acc_out=acc)
+    lib.qs_gemm_force_split(split)
     try:
-        for _ in range(3):  # repeated launches exercise the self-cleaning tile counters
+        for _ in range(2):
             out = torch.full((M, N), float("nan"), dtype=torch.half, device=dev)
             acc = torch.zeros((M, N), dtype=torch.int32, device=dev)
-            op.gemm_forward_cuda(*args, out, _acc_out=acc)
+            call(out, acc)
             torch.cuda.synchronize()
             assert np.array_equal(np_of(acc), acc_o)
             assert np.array_equal(bits16(np_of(out)), bits16(out_o))
     finally:
-        lib.qs_gemm_force_units_per_cta(0)
+        lib.qs_gemm_force_split(0)
 
 
 def test_llama3_8b_layer_shapes_decode_b64(dev):
