@@ -204,6 +204,11 @@ def _rows(t: torch.Tensor):
     return (t.numel() // hidden if hidden else 0), hidden
 
 
+def _noop(t: torch.Tensor) -> bool:
+    """Empty batches are a no-op (the reference launches a zero-sized grid); data_ptr() of an empty tensor is NULL."""
+    return t.numel() == 0
+
+
 def _half_only(t: torch.Tensor, op: str) -> None:
     _require(t.dtype == _HALF, f"{op}: only float16 activations are supported by qserve_b200 (models run .half(), model_runner.py:148)")
 
@@ -211,6 +216,8 @@ def _half_only(t: torch.Tensor, op: str) -> None:
 def rms_norm(out, input, weight, epsilon: float, use_quant: bool = False) -> None:
     """layernorm_ops.rms_norm (layernorm.cpp:48-50, layernorm_kernels.cu:404-425)."""
     _cuda(input, "input"); _half_only(input, "rms_norm")
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     check(lib.qs_rms_norm(out.data_ptr(), input.data_ptr(), weight.data_ptr(), float(epsilon), int(bool(use_quant)), tokens, hidden, _stream(input)))
 
@@ -218,6 +225,8 @@ def rms_norm(out, input, weight, epsilon: float, use_quant: bool = False) -> Non
 def rms_norm_general(out, input, weight, scaling, epsilon: float, use_per_token_quant: bool = False) -> None:
     """layernorm_ops.rms_norm_general (layernorm.cpp:52-54, layernorm_kernels.cu:427-464)."""
     _cuda(input, "input"); _half_only(input, "rms_norm_general")
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     check(lib.qs_rms_norm_general(out.data_ptr(), input.data_ptr(), weight.data_ptr(), scaling.data_ptr(), float(epsilon),
                                   int(bool(use_per_token_quant)), tokens, hidden, _stream(input)))
@@ -226,6 +235,8 @@ def rms_norm_general(out, input, weight, scaling, epsilon: float, use_per_token_
 def rms_norm_general_fuse_sum(out, input, weight, input_sum, scaling, epsilon: float, use_per_token_quant: bool = False) -> None:
     """layernorm_ops.rms_norm_general_fuse_sum (layernorm.cpp:56-58, layernorm_kernels.cu:466-508)."""
     _cuda(input, "input"); _half_only(input, "rms_norm_general_fuse_sum")
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     check(lib.qs_rms_norm_general_fuse_sum(out.data_ptr(), input.data_ptr(), weight.data_ptr(), input_sum.data_ptr(), scaling.data_ptr(),
                                            float(epsilon), int(bool(use_per_token_quant)), tokens, hidden, _stream(input)))
@@ -234,6 +245,8 @@ def rms_norm_general_fuse_sum(out, input, weight, input_sum, scaling, epsilon: f
 def invoke_dequant_add_residual_rms_norm_quant(out, input, residual, gamma, scale, epsilon: float) -> None:
     """layernorm_ops.invoke_dequant_add_residual_rms_norm_quant, scalar-Half and Tensor scale overloads (layernorm.cpp:60-71)."""
     _cuda(input, "input"); _half_only(residual, "invoke_dequant_add_residual_rms_norm_quant")
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
         check(lib.qs_dequant_add_residual_rms_norm_quant(out.data_ptr(), input.data_ptr(), residual.data_ptr(), gamma.data_ptr(), scale.data_ptr(), 0.0,
@@ -253,6 +266,8 @@ def invoke_quant(out, input, scale) -> None:
     """fused_kernels.invoke_quant: Tensor scale [tokens] (written) or scalar Half scale (read)  (fused.cpp:52-58)."""
     _cuda(input, "input"); _half_only(input, "invoke_quant")
     _require(input.is_contiguous() and out.is_contiguous(), "invoke_quant: input and out must be contiguous")  # asserts, fused_kernels.cu:202-203
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
         check(lib.qs_invoke_quant(out.data_ptr(), input.data_ptr(), scale.data_ptr(), tokens, hidden, _stream(input)))
@@ -265,6 +280,8 @@ def invoke_quant_fuse_sum(out, input, input_sum, scale) -> None:
     """fused_kernels.invoke_quant_fuse_sum (fused.cpp:59-69, fused_kernels.cu:234-265)."""
     _cuda(input, "input"); _half_only(input, "invoke_quant_fuse_sum")
     _require(input.is_contiguous() and out.is_contiguous(), "invoke_quant_fuse_sum: input and out must be contiguous")
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
         check(lib.qs_invoke_quant_fuse_sum(out.data_ptr(), input.data_ptr(), input_sum.data_ptr(), scale.data_ptr(), tokens, hidden, _stream(input)))
@@ -276,6 +293,8 @@ def invoke_quant_fuse_sum(out, input, input_sum, scale) -> None:
 def invoke_dequant_add_residual(out, input, residual, scale) -> None:
     """fused_kernels.invoke_dequant_add_residual, both overloads (fused.cpp:48-55)."""
     _cuda(input, "input"); _half_only(residual, "invoke_dequant_add_residual")
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
         check(lib.qs_invoke_dequant_add_residual(out.data_ptr(), input.data_ptr(), residual.data_ptr(), scale.data_ptr(), 0.0, tokens, hidden, _stream(input)))
@@ -287,6 +306,8 @@ def invoke_dequant_add_residual(out, input, residual, scale) -> None:
 def invoke_dequant(out, input, scale) -> None:
     """fused_kernels.invoke_dequant (fused.cpp:56, fused_kernels.cu:179-196)."""
     _cuda(input, "input"); _half_only(out, "invoke_dequant")
+    if _noop(input):
+        return
     tokens, hidden = _rows(input)
     s = float(torch.tensor(float(scale), dtype=_HALF))
     check(lib.qs_invoke_dequant(out.data_ptr(), input.data_ptr(), s, tokens, hidden, input.stride(-2), out.stride(-2), _stream(input)))
@@ -300,6 +321,8 @@ def invoke_dequant(out, input, scale) -> None:
 def silu_and_mul(out, input) -> None:
     """activation_ops.silu_and_mul (activation.cpp:26, activation_kernels.cu:84-97): out[..., d] = silu(x[..., :d]) * x[..., d:]."""
     _cuda(input, "input"); _half_only(input, "silu_and_mul")
+    if _noop(input):
+        return
     d = input.size(-1) // 2
     tokens = input.numel() // input.size(-1) if input.size(-1) else 0
     check(lib.qs_silu_and_mul(out.data_ptr(), input.data_ptr(), tokens, d, _stream(input)))

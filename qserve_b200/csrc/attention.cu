@@ -449,11 +449,10 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               // byte j of rows (a, b) -> half2(1024 + a_j, 1024 + b_j) - 1024
-              const uint32_t sel = static_cast<uint32_t>(j & 3) | 0x0080u | (static_cast<uint32_t>(4 + (j & 3)) << 8) | 0x8000u;
-              uint32_t b0 = __byte_perm(wa[j >> 2], wb[j >> 2], sel) | kMagic;
-              uint32_t b1 = __byte_perm(wc[j >> 2], wd[j >> 2], sel) | kMagic;
-              b0 = h2_sub(b0, kMagic);
-              b1 = h2_sub(b1, kMagic);
+              const uint32_t sel = static_cast<uint32_t>(j & 3) | (static_cast<uint32_t>(j & 3) << 4) | (static_cast<uint32_t>(4 + (j & 3)) << 8) |
+                                   (static_cast<uint32_t>(4 + (j & 3)) << 12);  // bytes [a_j, a_j, b_j, b_j]
+              const uint32_t b0 = h2_sub(lop3_and_or(__byte_perm(wa[j >> 2], wb[j >> 2], sel), 0x00ff00ffu, kMagic), kMagic);
+              const uint32_t b1 = h2_sub(lop3_and_or(__byte_perm(wc[j >> 2], wd[j >> 2], sel), 0x00ff00ffu, kMagic), kMagic);
               mma16816_acc(o[j][0], o[j][1], od0, od1, pa[0], pa[1], b0, b1);
             }
           }

@@ -35,7 +35,8 @@ namespace qs {
 namespace {
 
 constexpr int kBM = 128;  // output channels per tile (UMMA M)
-constexpr int kBK = 128;  // K per pipeline stage (= one g128 group)
+constexpr int kBK = 128;  // K sub-block (= one g128 group, one 128-byte swizzled activation row)
+constexpr int kSub = 2;    // sub-blocks per pipeline stage: per-stage barrier latencies are amortised over 256 K
 constexpr int kNumThreads = 192;
 constexpr int kEpiThreads = 128;
 
@@ -57,11 +58,15 @@ struct GemmParams {
 
 template <int MODE, int NT, int STAGES>
 struct Cfg {
-  static constexpr int kActBytes = NT * kBK;                                    // int8 activations, 128 B rows, swizzled
-  static constexpr int kWBytes = (MODE == kModeW8) ? kBM * kBK : kBM * kBK / 2; // int8 rows or packed int4 tiles
-  static constexpr int kS2Bytes = (MODE == kModeW4Grp) ? 2 * kBM : 0;           // scales | zeros for one group
+  static constexpr int kActSub = NT * kBK;                                       // one swizzled [NT x 128 B] activation sub-tile
+  static constexpr int kWSub = (MODE == kModeW8) ? kBM * kBK : kBM * kBK / 2;   // int8 rows or packed int4 tiles of one sub-block
+  static constexpr int kS2Sub = (MODE == kModeW4Grp) ? 2 * kBM : 0;             // scales | zeros of one group
+  static constexpr int kActBytes = kSub * kActSub;
+  static constexpr int kWBytes = kSub * kWSub;
+  static constexpr int kS2Bytes = kSub * kS2Sub;
   static constexpr int kStageTx = kActBytes + kWBytes + kS2Bytes;
-  static constexpr int kACols = (MODE == kModeW8) ? 0 : STAGES * (kBK / 4);     // TMEM columns of the unpacked-A ring
+  static constexpr int kAStageCols = kSub * (kBK / 4);                          // TMEM columns of one unpacked-A stage
+  static constexpr int kACols = (MODE == kModeW8) ? 0 : STAGES * kAStageCols;   // TMEM columns of the unpacked-A ring
   static constexpr int kTmemNeed = NT + kACols;
   static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "TMEM overflow");
@@ -146,7 +151,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   const int rank = (S > 1) ? static_cast<int>(cluster_ctarank()) : 0;
   const int tile = blockIdx.x / S;
   const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
-  // balanced K split: rank r owns k-blocks [kb_begin, kb_end)
+  // balanced K split: rank r owns pipeline stages (256 K each) [kb_begin, kb_end)
   const int KB = p.kb_per_tile;
   const int kb_begin = (KB * rank) / S, kb_end = (KB * (rank + 1)) / S;
   const int n_kb = kb_end - kb_begin;
@@ -177,33 +182,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       const int a_row = m_tile * NT;
       const uint8_t* s2s = p.s2_scales + static_cast<size_t>(n_tile) * kBM;
       const uint8_t* s2z = p.s2_zeros + static_cast<size_t>(n_tile) * kBM;
+      // one stage = kSub sub-blocks of 128 K.  A sub-block past the end of K (K % 256 == 128) is zero-filled by the
+      // tensor maps (weights and activations), so it contributes nothing; its g128 params are re-read from the last group.
+      auto issue_w = [&](int st, int s) {
+        mbar_expect_tx(&bar_full[s], C::kStageTx);
+#pragma unroll
+        for (int u = 0; u < kSub; ++u) {
+          const int kb = (kb_begin + st) * kSub + u;
+          // W4: u64 elements, 256 per 128-K block of one band (4 tiles x 512 B); W8: bytes
+          tma_load_2d(s_w + s * C::kWBytes + u * C::kWSub, &tmap_w, (MODE == kModeW8) ? kb * kBK : kb * 256, w_row, &bar_full[s]);
+          if constexpr (MODE == kModeW4Grp) {
+            const int kg = kb < p.K / kBK ? kb : p.K / kBK - 1;
+            bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub, s2s + static_cast<size_t>(kg) * p.N, kBM, &bar_full[s]);
+            bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub + kBM, s2z + static_cast<size_t>(kg) * p.N, kBM, &bar_full[s]);
+          }
+        }
+      };
+      auto issue_a = [&](int st, int s) {
+#pragma unroll
+        for (int u = 0; u < kSub; ++u)
+          tma_load_2d(s_act + s * C::kActBytes + u * C::kActSub, &tmap_act, ((kb_begin + st) * kSub + u) * kBK, a_row, &bar_full[s]);
+      };
       // static weights do not depend on the previous kernel: prefetch a full ring before the PDL wait
       const int pre = n_kb < STAGES ? n_kb : STAGES;
-      for (int it = 0; it < pre; ++it) {
-        const int kb = kb_begin + it;
-        mbar_expect_tx(&bar_full[it], C::kStageTx);
-        // W4: u64 elements, 256 per 128-K block of one band (4 tiles x 512 B); W8: bytes
-        tma_load_2d(s_w + it * C::kWBytes, &tmap_w, (MODE == kModeW8) ? kb * kBK : kb * 256, w_row, &bar_full[it]);
-        if constexpr (MODE == kModeW4Grp) {
-          bulk_copy_g2s(s_s2 + it * C::kS2Bytes, s2s + static_cast<size_t>(kb) * p.N, kBM, &bar_full[it]);
-          bulk_copy_g2s(s_s2 + it * C::kS2Bytes + kBM, s2z + static_cast<size_t>(kb) * p.N, kBM, &bar_full[it]);
-        }
-      }
+      for (int it = 0; it < pre; ++it) issue_w(it, it);
       pdl_wait();
       QS_PROF(2);
-      for (int it = 0; it < pre; ++it) tma_load_2d(s_act + it * C::kActBytes, &tmap_act, (kb_begin + it) * kBK, a_row, &bar_full[it]);
+      for (int it = 0; it < pre; ++it) issue_a(it, it);
       int s = 0;
       uint32_t ph = 0;  // parity of the (it / STAGES - 1)-th completion of empty[s]
       for (int it = pre; it < n_kb; ++it) {
-        const int kb = kb_begin + it;
         mbar_wait(&bar_empty[s], ph);
-        mbar_expect_tx(&bar_full[s], C::kStageTx);
-        tma_load_2d(s_w + s * C::kWBytes, &tmap_w, (MODE == kModeW8) ? kb * kBK : kb * 256, w_row, &bar_full[s]);
-        if constexpr (MODE == kModeW4Grp) {
-          bulk_copy_g2s(s_s2 + s * C::kS2Bytes, s2s + static_cast<size_t>(kb) * p.N, kBM, &bar_full[s]);
-          bulk_copy_g2s(s_s2 + s * C::kS2Bytes + kBM, s2z + static_cast<size_t>(kb) * p.N, kBM, &bar_full[s]);
-        }
-        tma_load_2d(s_act + s * C::kActBytes, &tmap_act, kb * kBK, a_row, &bar_full[s]);
+        issue_w(it, s);
+        issue_a(it, s);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       QS_PROF(3);
@@ -215,19 +226,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < n_kb; ++it) {
-        mbar_wait(&bar_full[s], ph);
+        // W4: the unpack warps observed full[s] before arriving on afull[s], so afull[s] alone orders the TMA data
+        if constexpr (MODE == kModeW8) mbar_wait(&bar_full[s], ph); else mbar_wait(&bar_afull[s], ph);
         if (it == 0) QS_PROF(4);
-        if constexpr (MODE != kModeW8) mbar_wait(&bar_afull[s], ph);
         tc_fence_after();
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + s * C::kActBytes));
 #pragma unroll
-        for (int t = 0; t < kBK / 32; ++t) {
-          const uint32_t acc = (it > 0 || t > 0) ? 1u : 0u;
-          if constexpr (MODE == kModeW8) {
-            const uint64_t adesc = umma_desc_sw128(smem_u32(s_w + s * C::kWBytes));
-            umma_i8_ss(tmem_base, adesc + t * 2, bdesc + t * 2, idesc, acc);
-          } else {
-            umma_i8_ts(tmem_base, tmem_base + NT + s * (kBK / 4) + t * 8, bdesc + t * 2, idesc, acc);
+        for (int u = 0; u < kSub; ++u) {
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + s * C::kActBytes + u * C::kActSub));
+#pragma unroll
+          for (int t = 0; t < kBK / 32; ++t) {
+            const uint32_t acc = (it > 0 || u > 0 || t > 0) ? 1u : 0u;
+            if constexpr (MODE == kModeW8) {
+              const uint64_t adesc = umma_desc_sw128(smem_u32(s_w + s * C::kWBytes + u * C::kWSub));
+              umma_i8_ss(tmem_base, adesc + t * 2, bdesc + t * 2, idesc, acc);
+            } else {
+              umma_i8_ts(tmem_base, tmem_base + NT + s * C::kAStageCols + u * (kBK / 4) + t * 8, bdesc + t * 2, idesc, acc);
+            }
           }
         }
         umma_commit(&bar_empty[s]);
@@ -245,34 +259,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       uint32_t ph = 0;
       for (int it = 0; it < n_kb; ++it) {
         mbar_wait(&bar_full[s], ph);
-        const uint8_t* wsrc = s_w + s * C::kWBytes + quad * 2048 + lane * 16;
-        const uint32_t tdst = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + NT + s * (kBK / 4);
-        uint32_t sc4 = 0, zp4 = 0;
-        if constexpr (MODE == kModeW4Grp) {
-          const uint8_t* s2 = s_s2 + s * C::kS2Bytes + quad * 32 + (lane >> 2) * 4;
-          sc4 = *reinterpret_cast<const uint32_t*>(s2);
-          zp4 = *reinterpret_cast<const uint32_t*>(s2 + kBM);
-        }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint4 v = *reinterpret_cast<const uint4*>(wsrc + t * 512);
-          uint32_t xl = v.x & 0x0F0F0F0Fu, xh = (v.x >> 4) & 0x0F0F0F0Fu;
-          uint32_t yl = v.y & 0x0F0F0F0Fu, yh = (v.y >> 4) & 0x0F0F0F0Fu;
-          uint32_t zl = v.z & 0x0F0F0F0Fu, zh = (v.z >> 4) & 0x0F0F0F0Fu;
-          uint32_t wl = v.w & 0x0F0F0F0Fu, wh = (v.w >> 4) & 0x0F0F0F0Fu;
+        for (int u = 0; u < kSub; ++u) {
+          const uint8_t* wsrc = s_w + s * C::kWBytes + u * C::kWSub + quad * 2048 + lane * 16;
+          const uint32_t tdst = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + NT + s * C::kAStageCols + u * (kBK / 4);
+          uint32_t sc4 = 0, zp4 = 0;
           if constexpr (MODE == kModeW4Grp) {
-            // w4a8_per_group/gemm_cuda.cu:298-324: 32-bit multiply of four nibble-bytes, then vadd4 with the s8 zero
-            const uint32_t s0 = sc4 & 0xFF, s1 = (sc4 >> 8) & 0xFF, s2 = (sc4 >> 16) & 0xFF, s3 = sc4 >> 24;
-            const uint32_t z0 = __byte_perm(zp4, 0, 0x0000), z1 = __byte_perm(zp4, 0, 0x1111);
-            const uint32_t z2 = __byte_perm(zp4, 0, 0x2222), z3 = __byte_perm(zp4, 0, 0x3333);
-            xl = __vadd4(xl * s0, z0); zl = __vadd4(zl * s0, z0);   // channel c
-            yl = __vadd4(yl * s1, z1); wl = __vadd4(wl * s1, z1);   // channel c + 8
-            xh = __vadd4(xh * s2, z2); zh = __vadd4(zh * s2, z2);   // channel c + 16
-            yh = __vadd4(yh * s3, z3); wh = __vadd4(wh * s3, z3);   // channel c + 24
+            const uint8_t* s2 = s_s2 + s * C::kS2Bytes + u * C::kS2Sub + quad * 32 + (lane >> 2) * 4;
+            sc4 = *reinterpret_cast<const uint32_t*>(s2);
+            zp4 = *reinterpret_cast<const uint32_t*>(s2 + kBM);
           }
-          // lanes 0..15 of the quadrant <- channels c, c+8 ; lanes 16..31 <- channels c+16, c+24 ; 8 columns = 32 k
-          tmem_st_16x128b_x2(tdst + t * 8, xl, yl, zl, wl);
-          tmem_st_16x128b_x2(tdst + t * 8 + (16u << 16), xh, yh, zh, wh);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint4 v = *reinterpret_cast<const uint4*>(wsrc + t * 512);
+            uint32_t xl = v.x & 0x0F0F0F0Fu, xh = (v.x >> 4) & 0x0F0F0F0Fu;
+            uint32_t yl = v.y & 0x0F0F0F0Fu, yh = (v.y >> 4) & 0x0F0F0F0Fu;
+            uint32_t zl = v.z & 0x0F0F0F0Fu, zh = (v.z >> 4) & 0x0F0F0F0Fu;
+            uint32_t wl = v.w & 0x0F0F0F0Fu, wh = (v.w >> 4) & 0x0F0F0F0Fu;
+            if constexpr (MODE == kModeW4Grp) {
+              // w4a8_per_group/gemm_cuda.cu:298-324: 32-bit multiply of four nibble-bytes, then vadd4 with the s8 zero
+              const uint32_t s0 = sc4 & 0xFF, s1 = (sc4 >> 8) & 0xFF, s2 = (sc4 >> 16) & 0xFF, s3 = sc4 >> 24;
+              const uint32_t z0 = __byte_perm(zp4, 0, 0x0000), z1 = __byte_perm(zp4, 0, 0x1111);
+              const uint32_t z2 = __byte_perm(zp4, 0, 0x2222), z3 = __byte_perm(zp4, 0, 0x3333);
+              xl = __vadd4(xl * s0, z0); zl = __vadd4(zl * s0, z0);   // channel c
+              yl = __vadd4(yl * s1, z1); wl = __vadd4(wl * s1, z1);   // channel c + 8
+              xh = __vadd4(xh * s2, z2); zh = __vadd4(zh * s2, z2);   // channel c + 16
+              yh = __vadd4(yh * s3, z3); wh = __vadd4(wh * s3, z3);   // channel c + 24
+            }
+            // lanes 0..15 of the quadrant <- channels c, c+8 ; lanes 16..31 <- channels c+16, c+24 ; 8 columns = 32 k
+            tmem_st_16x128b_x2(tdst + t * 8, xl, yl, zl, wl);
+            tmem_st_16x128b_x2(tdst + t * 8 + (16u << 16), xh, yh, zh, wh);
+          }
         }
         tmem_wait_st();
         tc_fence_before();
@@ -321,8 +338,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
     uint32_t red_peer[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) red_peer[r] = (S > 1 && r < S) ? map_to_cta(red_local, r) : red_local;
-    for (int idx = epi_tid; idx < npairs * NT; idx += kEpiThreads) {
-      const int pr = pair0 + idx % npairs, tok = idx / npairs;
+    // npairs divides 128, so a thread keeps one channel pair and walks the tokens
+    const int pr = pair0 + epi_tid % npairs;
+    const int tstep = kEpiThreads / npairs;
+    const int n = n_tile * kBM + 2 * pr;
+    const __half2 ws = *reinterpret_cast<const __half2*>(p.wscales + n);
+    float wz0 = 0.f, wz1 = 0.f;
+    if constexpr (MODE == kModeW4Chn) {
+      const __half2 wz = *reinterpret_cast<const __half2*>(p.w_szs + n);
+      wz0 = __low2float(wz); wz1 = __high2float(wz);
+    }
+    const float ws0 = __low2float(ws), ws1 = __high2float(ws);
+#pragma unroll 4
+    for (int tok = epi_tid / npairs; tok < NT; tok += tstep) {
       const int m = m0 + tok;
       const uint32_t off = static_cast<uint32_t>((tok * kBM + 2 * pr) * 4);
       int2 acc = make_int2(0, 0);
@@ -339,16 +367,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
         }
       }
       if (m < p.M) {
-        const int n = n_tile * kBM + 2 * pr;
-        const __half2 ws = *reinterpret_cast<const __half2*>(p.wscales + n);
-        float wz0 = 0.f, wz1 = 0.f;
-        if constexpr (MODE == kModeW4Chn) {
-          const __half2 wz = *reinterpret_cast<const __half2*>(p.w_szs + n);
-          wz0 = __low2float(wz); wz1 = __high2float(wz);
-        }
         const float as = s_asc[tok], asum = s_asum[tok];
-        const __half o0 = epilogue_one<MODE>(acc.x, __low2float(ws), wz0, as, asum);
-        const __half o1 = epilogue_one<MODE>(acc.y, __high2float(ws), wz1, as, asum);
+        const __half o0 = epilogue_one<MODE>(acc.x, ws0, wz0, as, asum);
+        const __half o1 = epilogue_one<MODE>(acc.y, ws1, wz1, as, asum);
         *reinterpret_cast<__half2*>(p.out + static_cast<size_t>(m) * p.N + n) = __halves2half2(o0, o1);
         if (p.acc_out) *reinterpret_cast<int2*>(p.acc_out + static_cast<size_t>(m) * p.N + n) = acc;
       }
@@ -427,7 +448,7 @@ int choose_split(int tiles, int kb_per_tile, int forced) {
   } else {
     const int sms = num_sms();
     // smallest power of two that brings the CTA count to >= ~2/3 of the SMs; every CTA keeps >= 2 k-blocks
-    while (s < 8 && tiles * s < (2 * sms) / 3 && kb_per_tile / (2 * s) >= 2) s *= 2;
+    while (s < 8 && tiles * s < (2 * sms) / 3 && kb_per_tile / (2 * s) >= 1) s *= 2;
   }
   if (s > 8) s = 8;
   while (s > 1 && kb_per_tile < s) s /= 2;
@@ -450,7 +471,7 @@ int launch_gemm(const GemmArgs& a) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   const int n_tiles = a.N / kBM;
   p.m_tiles = (a.M + NT - 1) / NT;
-  p.kb_per_tile = a.K / kBK;
+  p.kb_per_tile = (a.K + kSub * kBK - 1) / (kSub * kBK);  // pipeline stages of 256 K (the last one may be half zero-filled)
   const int tiles = n_tiles * p.m_tiles;
   p.split = choose_split(tiles, p.kb_per_tile, a.force_split);
 
@@ -491,10 +512,11 @@ int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.K % kBK == 0, "gemm: K=%d must be a multiple of %d", a.K, kBK);
   QS_REQUIRE((reinterpret_cast<uintptr_t>(a.act) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.weight) & 15) == 0, "gemm: operands must be 16-byte aligned");
   QS_REQUIRE(a.force_split == 0 || a.force_split == 1 || a.force_split == 2 || a.force_split == 4 || a.force_split == 8, "gemm: split must be 1, 2, 4 or 8");
-  if (a.M <= 32) return launch_gemm<MODE, 32, (MODE == kModeW8 ? 4 : 6)>(a);
-  if (a.M <= 64) return launch_gemm<MODE, 64, (MODE == kModeW8 ? 4 : 6)>(a);
-  if (a.M <= 128) return launch_gemm<MODE, 128, (MODE == kModeW8 ? 3 : 4)>(a);
-  return launch_gemm<MODE, 256, (MODE == kModeW8 ? 4 : 5)>(a);
+  // stages are 256 K deep; counts chosen so that NT <= 128 fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns)
+  if (a.M <= 32) return launch_gemm<MODE, 32, (MODE == kModeW8 ? 2 : 3)>(a);
+  if (a.M <= 64) return launch_gemm<MODE, 64, (MODE == kModeW8 ? 2 : 3)>(a);
+  if (a.M <= 128) return launch_gemm<MODE, 128, 2>(a);
+  return launch_gemm<MODE, 256, 2>(a);
 }
 
 }  // namespace
