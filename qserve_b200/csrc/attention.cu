@@ -124,12 +124,19 @@ struct StageLayout {
   static constexpr int kStages = (BITS == 4) ? 4 : 3;
 };
 
-// mma.sync m16n8k16 with explicit accumulator registers (rows 8..15 of A are zero)
-__device__ __forceinline__ void mma16816_acc(float& c0, float& c1, float& c2, float& c3, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+// full m16n8k16: all four A registers and all four accumulators carry data
+__device__ __forceinline__ void mma_full(float& c0, float& c1, float& c2, float& c3, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
-      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// 8x8 b16 transpose across the warp: thread t holds (row t/4, cols 2(t%4), 2(t%4)+1) before and after
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(x));
+  return d;
 }
 
 template <int BITS>
@@ -272,9 +279,9 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       }
     }
 
-    // ---- Q operand fragments, permuted to the in-register order of the unpacked codes; sum(q) per row ----
-    uint32_t qa0[8], qa2[8];
-    float sumq;
+    // ---- Q as the MMA "B" operand (n = head g), permuted to the in-register order of the unpacked codes; sum(q) per head ----
+    uint32_t qb0[8], qb1[8];
+    float sumq0, sumq1;  // heads 2*q4 and 2*q4+1 (this thread's S^T columns)
     {
       const __half* qr = s_q + g * kD + 32 * q4;
       float acc = 0.f;
@@ -282,31 +289,31 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       for (int j = 0; j < 32; ++j) acc += __half2float(qr[j]);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      sumq = acc;
+      sumq0 = __shfl_sync(0xffffffffu, acc, (2 * q4) * 4);
+      sumq1 = __shfl_sync(0xffffffffu, acc, (2 * q4 + 1) * 4);
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         if constexpr (BITS == 4) {
           const int d0 = 8 * (s >> 1) + 2 * (s & 1);  // k-step 2w: nibbles (0,4 | 1,5); 2w+1: (2,6 | 3,7) of word w
-          qa0[s] = pack_h2(qr[d0], qr[d0 + 4]);
-          qa2[s] = pack_h2(qr[d0 + 1], qr[d0 + 5]);
+          qb0[s] = pack_h2(qr[d0], qr[d0 + 4]);
+          qb1[s] = pack_h2(qr[d0 + 1], qr[d0 + 5]);
         } else {
-          qa0[s] = pack_h2(qr[4 * s], qr[4 * s + 1]);
-          qa2[s] = pack_h2(qr[4 * s + 2], qr[4 * s + 3]);
+          qb0[s] = pack_h2(qr[4 * s], qr[4 * s + 1]);
+          qb1[s] = pack_h2(qr[4 * s + 2], qr[4 * s + 3]);
         }
       }
     }
 
     const float sm_scale = rsqrtf(static_cast<float>(kD)) * 1.4426950408889634f;  // 1/sqrt(D) * log2(e)
-    float o[16][2];
-    float od0 = 0.f, od1 = 0.f;
+    // O^T accumulators: m-tile i (dims 16g + 2i, 16g + 2i + 1) x heads (2q4, 2q4+1)
+    float o[8][4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j][0] = o[j][1] = 0.f;
-    float m_run = -CUDART_INF_F, l_run = 0.f, c_run = 0.f;  // running max (log2 units), sum of p, sum of p * c_v
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f, cr0 = 0.f, cr1 = 0.f;
 
-    // S column c of n-tile nt <-> chunk token nt*8 + (c&1)*4 + (c>>1)   (keeps the V row reads at a 2-way bank conflict)
-    const int tokA = (g & 1) * 4 + (g >> 1);       // K row this lane loads for n-tile 0 (n-tile 1: + 8)
-    const int c0 = 2 * q4, c1 = 2 * q4 + 1;        // this lane's S / P columns
-    const int tk0 = (c0 & 1) * 4 + (c0 >> 1), tk1 = (c1 & 1) * 4 + (c1 >> 1);  // tokens of columns c0, c1 inside an n-tile
+    // S^T = K Q^T: A rows g / g+8 <-> chunk tokens tokA / 8+tokA (the permutation keeps the V row reads at a 2-way conflict)
+    const int tokA = (g & 1) * 4 + (g >> 1);
+    constexpr int kRow = kD * BITS / 8;  // bytes per token row
 
     int s = 0;
     uint32_t ph = 0;
@@ -327,101 +334,84 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
           s_meta[s][lane >> 4][warp * kChunk + tl] = packed;
         }
         __syncwarp();
-        // ---- S = Q K^T on raw codes ----
-        float sacc[2][4];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-          const uint8_t* krow = st + SL::kOffK + (warp * kChunk + nt * 8 + tokA) * (kD * BITS / 8);
+        // ---- S^T (16 tokens x 8 heads) on raw codes: 8 MMAs ----
+        float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
+        {
+          const uint8_t* krow = st + SL::kOffK + (warp * kChunk + tokA) * kRow;
           if constexpr (BITS == 4) {
-            const uint4 kv = *reinterpret_cast<const uint4*>(krow + q4 * 16);
-            const uint32_t wds[4] = {kv.x, kv.y, kv.z, kv.w};
+            const uint4 ka = *reinterpret_cast<const uint4*>(krow + q4 * 16);
+            const uint4 kb = *reinterpret_cast<const uint4*>(krow + 8 * kRow + q4 * 16);
+            const uint32_t wa[4] = {ka.x, ka.y, ka.z, ka.w}, wb[4] = {kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-              const uint32_t x = wds[w], top = x >> 8;
-              const uint32_t e0 = h2_sub(lop3_and_or(x, 0x000f000fu, kMagic), kMagic);
-              const uint32_t e1 = h2_fma(lop3_and_or(x, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-              const uint32_t e2 = h2_sub(lop3_and_or(top, 0x000f000fu, kMagic), kMagic);
-              const uint32_t e3 = h2_fma(lop3_and_or(top, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-              mma16816_acc(sacc[nt][0], sacc[nt][1], sacc[nt][2], sacc[nt][3], qa0[2 * w], qa2[2 * w], e0, e1);
-              mma16816_acc(sacc[nt][0], sacc[nt][1], sacc[nt][2], sacc[nt][3], qa0[2 * w + 1], qa2[2 * w + 1], e2, e3);
+              const uint32_t xa = wa[w], xb = wb[w], ta = xa >> 8, tb = xb >> 8;
+              mma_full(sc0, sc1, sc2, sc3, h2_sub(lop3_and_or(xa, 0x000f000fu, kMagic), kMagic), h2_sub(lop3_and_or(xb, 0x000f000fu, kMagic), kMagic),
+                       h2_fma(lop3_and_or(xa, 0x00f000f0u, kMagic), kSixteenth, kNeg64), h2_fma(lop3_and_or(xb, 0x00f000f0u, kMagic), kSixteenth, kNeg64),
+                       qb0[2 * w], qb1[2 * w]);
+              mma_full(sc0, sc1, sc2, sc3, h2_sub(lop3_and_or(ta, 0x000f000fu, kMagic), kMagic), h2_sub(lop3_and_or(tb, 0x000f000fu, kMagic), kMagic),
+                       h2_fma(lop3_and_or(ta, 0x00f000f0u, kMagic), kSixteenth, kNeg64), h2_fma(lop3_and_or(tb, 0x00f000f0u, kMagic), kSixteenth, kNeg64),
+                       qb0[2 * w + 1], qb1[2 * w + 1]);
             }
           } else {
-            const uint4 ka = *reinterpret_cast<const uint4*>(krow + q4 * 32);
-            const uint4 kb = *reinterpret_cast<const uint4*>(krow + q4 * 32 + 16);
-            const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+            const uint4 ka0 = *reinterpret_cast<const uint4*>(krow + q4 * 32), ka1 = *reinterpret_cast<const uint4*>(krow + q4 * 32 + 16);
+            const uint4 kb0 = *reinterpret_cast<const uint4*>(krow + 8 * kRow + q4 * 32), kb1 = *reinterpret_cast<const uint4*>(krow + 8 * kRow + q4 * 32 + 16);
+            const uint32_t wa[8] = {ka0.x, ka0.y, ka0.z, ka0.w, ka1.x, ka1.y, ka1.z, ka1.w};
+            const uint32_t wb[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-              // bytes -> fp16 integers: 0x6400 | u  = 1024 + u, minus 1024 (exact)
-              const uint32_t e0 = h2_sub(__byte_perm(wds[w], kMagic, 0x7150), kMagic);
-              const uint32_t e1 = h2_sub(__byte_perm(wds[w], kMagic, 0x7352), kMagic);
-              mma16816_acc(sacc[nt][0], sacc[nt][1], sacc[nt][2], sacc[nt][3], qa0[w], qa2[w], e0, e1);
+              // bytes -> fp16 integers: 0x6400 | u = 1024 + u, minus 1024 (exact)
+              mma_full(sc0, sc1, sc2, sc3, h2_sub(__byte_perm(wa[w], kMagic, 0x7150), kMagic), h2_sub(__byte_perm(wb[w], kMagic, 0x7150), kMagic),
+                       h2_sub(__byte_perm(wa[w], kMagic, 0x7352), kMagic), h2_sub(__byte_perm(wb[w], kMagic, 0x7352), kMagic), qb0[w], qb1[w]);
             }
           }
         }
-        // ---- logits (log2 units) for row g, columns c0, c1 of both n-tiles; online softmax with lazy rescale ----
-        float t[2][2];
-        float cmax = -CUDART_INF_F;
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const uint32_t m0 = s_meta[s][0][warp * kChunk + nt * 8 + tk0], m1 = s_meta[s][0][warp * kChunk + nt * 8 + tk1];
-          float sc0, sc1, cc0, cc1;
-          sc0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 & 0xFFFF)));
-          sc1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 & 0xFFFF)));
-          if constexpr (BITS == 4) {
-            cc0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
-            cc1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
-          } else {
-            cc0 = -sc0 * __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
-            cc1 = -sc1 * __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
-          }
-          const bool ok0 = (t0 + nt * 8 + tk0) < tlen, ok1 = (t0 + nt * 8 + tk1) < tlen;
-          t[nt][0] = ok0 ? (sc0 * sacc[nt][0] + cc0 * sumq) * sm_scale : -CUDART_INF_F;
-          t[nt][1] = ok1 ? (sc1 * sacc[nt][1] + cc1 * sumq) * sm_scale : -CUDART_INF_F;
-          cmax = fmaxf(cmax, fmaxf(t[nt][0], t[nt][1]));
+        // ---- logits (log2 units) of tokens A = tokA, B = 8 + tokA for heads 2q4, 2q4+1; online softmax with lazy rescale ----
+        const uint32_t mkA = s_meta[s][0][warp * kChunk + tokA], mkB = s_meta[s][0][warp * kChunk + 8 + tokA];
+        const uint32_t mvA = s_meta[s][1][warp * kChunk + tokA], mvB = s_meta[s][1][warp * kChunk + 8 + tokA];
+        const float ksA = __half2float(__ushort_as_half(static_cast<uint16_t>(mkA & 0xFFFF))), ksB = __half2float(__ushort_as_half(static_cast<uint16_t>(mkB & 0xFFFF)));
+        const float vsA = __half2float(__ushort_as_half(static_cast<uint16_t>(mvA & 0xFFFF))), vsB = __half2float(__ushort_as_half(static_cast<uint16_t>(mvB & 0xFFFF)));
+        float kcA = __half2float(__ushort_as_half(static_cast<uint16_t>(mkA >> 16))), kcB = __half2float(__ushort_as_half(static_cast<uint16_t>(mkB >> 16)));
+        float vcA = __half2float(__ushort_as_half(static_cast<uint16_t>(mvA >> 16))), vcB = __half2float(__ushort_as_half(static_cast<uint16_t>(mvB >> 16)));
+        if constexpr (BITS == 8) {  // aux holds the zero point: c = -s * z
+          kcA = -ksA * kcA; kcB = -ksB * kcB; vcA = -vsA * vcA; vcB = -vsB * vcB;
         }
-        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
-        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
-        const bool need = cmax > m_run + 8.f;  // rescale only when the running max moves by more than 2^8
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? exp2f(m_run - cmax) : 1.f;
-          if (need) m_run = cmax;
-          l_run *= alpha;
-          c_run *= alpha;
+        const bool okA = (t0 + tokA) < tlen, okB = (t0 + 8 + tokA) < tlen;
+        const float tA0 = okA ? (ksA * sc0 + kcA * sumq0) * sm_scale : -CUDART_INF_F;
+        const float tA1 = okA ? (ksA * sc1 + kcA * sumq1) * sm_scale : -CUDART_INF_F;
+        const float tB0 = okB ? (ksB * sc2 + kcB * sumq0) * sm_scale : -CUDART_INF_F;
+        const float tB1 = okB ? (ksB * sc3 + kcB * sumq1) * sm_scale : -CUDART_INF_F;
+        float mh0 = fmaxf(tA0, tB0), mh1 = fmaxf(tA1, tB1);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            o[j][0] *= alpha;
-            o[j][1] *= alpha;
+        for (int m = 4; m <= 16; m <<= 1) {
+          mh0 = fmaxf(mh0, __shfl_xor_sync(0xffffffffu, mh0, m));
+          mh1 = fmaxf(mh1, __shfl_xor_sync(0xffffffffu, mh1, m));
+        }
+        const bool n0 = mh0 > m0 + 8.f, n1 = mh1 > m1 + 8.f;  // rescale only when a running max moves by more than 2^8
+        if (__any_sync(0xffffffffu, n0 || n1)) {
+          const float a0 = n0 ? exp2f(m0 - mh0) : 1.f, a1 = n1 ? exp2f(m1 - mh1) : 1.f;
+          if (n0) m0 = mh0;
+          if (n1) m1 = mh1;
+          l0 *= a0; cr0 *= a0; l1 *= a1; cr1 *= a1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i][0] *= a0; o[i][2] *= a0;
+            o[i][1] *= a1; o[i][3] *= a1;
           }
         }
-        // ---- P' = p * s_v ;  c_run += p * c_v ----
-        uint32_t pa[2];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const uint32_t m0 = s_meta[s][1][warp * kChunk + nt * 8 + tk0], m1 = s_meta[s][1][warp * kChunk + nt * 8 + tk1];
-          const float p0 = exp2f(t[nt][0] - m_run), p1 = exp2f(t[nt][1] - m_run);
-          const float sv0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 & 0xFFFF)));
-          const float sv1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 & 0xFFFF)));
-          float cv0, cv1;
-          if constexpr (BITS == 4) {
-            cv0 = __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
-            cv1 = __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
-          } else {
-            cv0 = -sv0 * __half2float(__ushort_as_half(static_cast<uint16_t>(m0 >> 16)));
-            cv1 = -sv1 * __half2float(__ushort_as_half(static_cast<uint16_t>(m1 >> 16)));
-          }
-          l_run += p0 + p1;
-          c_run += p0 * cv0 + p1 * cv1;
-          pa[nt] = pack_f2h2(p0 * sv0, p1 * sv1);
-        }
-        // ---- O += P' V on raw codes; MMA k index (2q4, 2q4+1 | +8) <-> S columns c0, c1 of n-tile 0 | 1 ----
+        const float pA0 = exp2f(tA0 - m0), pA1 = exp2f(tA1 - m1), pB0 = exp2f(tB0 - m0), pB1 = exp2f(tB1 - m1);
+        l0 += pA0 + pB0; l1 += pA1 + pB1;
+        cr0 += pA0 * vcA + pB0 * vcB; cr1 += pA1 * vcA + pB1 * vcB;
+        // P'^T fragments: transpose the (token, head) tiles so that tokens become the MMA k index
+        const uint32_t bp0 = movmatrix_trans(pack_f2h2(pA0 * vsA, pA1 * vsA));  // k = 2q4, 2q4+1  <-> chunk tokens q4, 4+q4
+        const uint32_t bp1 = movmatrix_trans(pack_f2h2(pB0 * vsB, pB1 * vsB));  // k = 2q4+8, +9   <-> chunk tokens 8+q4, 12+q4
+        // ---- O^T += V^T P'^T on raw codes: 8 MMAs (m-tile = 16 dims) ----
         {
-          const uint8_t* vbase = st + SL::kOffV + (warp * kChunk) * (kD * BITS / 8);
+          const uint8_t* vbase = st + SL::kOffV + (warp * kChunk + q4) * kRow;
           if constexpr (BITS == 4) {
-            const uint2 va = *reinterpret_cast<const uint2*>(vbase + tk0 * 64 + g * 8);
-            const uint2 vb = *reinterpret_cast<const uint2*>(vbase + tk1 * 64 + g * 8);
-            const uint2 vc = *reinterpret_cast<const uint2*>(vbase + (8 + tk0) * 64 + g * 8);
-            const uint2 vd = *reinterpret_cast<const uint2*>(vbase + (8 + tk1) * 64 + g * 8);
+            const uint2 va = *reinterpret_cast<const uint2*>(vbase + g * 8);
+            const uint2 vb = *reinterpret_cast<const uint2*>(vbase + 4 * kRow + g * 8);
+            const uint2 vc = *reinterpret_cast<const uint2*>(vbase + 8 * kRow + g * 8);
+            const uint2 vd = *reinterpret_cast<const uint2*>(vbase + 12 * kRow + g * 8);
 #pragma unroll
             for (int ww = 0; ww < 2; ++ww) {
               const uint32_t a = ww ? va.y : va.x, bb = ww ? vb.y : vb.x, cc = ww ? vc.y : vc.x, dd = ww ? vd.y : vd.x;
@@ -430,30 +420,29 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
                 const uint32_t sel = static_cast<uint32_t>(kb) | (static_cast<uint32_t>(kb) << 4) | (static_cast<uint32_t>(4 + kb) << 8) |
                                      (static_cast<uint32_t>(4 + kb) << 12);  // bytes [a_kb, a_kb, b_kb, b_kb]
                 const uint32_t m01 = __byte_perm(a, bb, sel), m89 = __byte_perm(cc, dd, sel);
-                const uint32_t lo01 = h2_sub(lop3_and_or(m01, 0x000f000fu, kMagic), kMagic);
-                const uint32_t hi01 = h2_fma(lop3_and_or(m01, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-                const uint32_t lo89 = h2_sub(lop3_and_or(m89, 0x000f000fu, kMagic), kMagic);
-                const uint32_t hi89 = h2_fma(lop3_and_or(m89, 0x00f000f0u, kMagic), kSixteenth, kNeg64);
-                const int j = 8 * ww + 2 * kb;
-                mma16816_acc(o[j][0], o[j][1], od0, od1, pa[0], pa[1], lo01, lo89);
-                mma16816_acc(o[j + 1][0], o[j + 1][1], od0, od1, pa[0], pa[1], hi01, hi89);
+                const int i = 4 * ww + kb;
+                mma_full(o[i][0], o[i][1], o[i][2], o[i][3], h2_sub(lop3_and_or(m01, 0x000f000fu, kMagic), kMagic),
+                         h2_fma(lop3_and_or(m01, 0x00f000f0u, kMagic), kSixteenth, kNeg64), h2_sub(lop3_and_or(m89, 0x000f000fu, kMagic), kMagic),
+                         h2_fma(lop3_and_or(m89, 0x00f000f0u, kMagic), kSixteenth, kNeg64), bp0, bp1);
               }
             }
           } else {
-            const uint4 va = *reinterpret_cast<const uint4*>(vbase + tk0 * 128 + g * 16);
-            const uint4 vb = *reinterpret_cast<const uint4*>(vbase + tk1 * 128 + g * 16);
-            const uint4 vc = *reinterpret_cast<const uint4*>(vbase + (8 + tk0) * 128 + g * 16);
-            const uint4 vd = *reinterpret_cast<const uint4*>(vbase + (8 + tk1) * 128 + g * 16);
+            const uint4 va = *reinterpret_cast<const uint4*>(vbase + g * 16);
+            const uint4 vb = *reinterpret_cast<const uint4*>(vbase + 4 * kRow + g * 16);
+            const uint4 vc = *reinterpret_cast<const uint4*>(vbase + 8 * kRow + g * 16);
+            const uint4 vd = *reinterpret_cast<const uint4*>(vbase + 12 * kRow + g * 16);
             const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
             const uint32_t wc[4] = {vc.x, vc.y, vc.z, vc.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              // byte j of rows (a, b) -> half2(1024 + a_j, 1024 + b_j) - 1024
-              const uint32_t sel = static_cast<uint32_t>(j & 3) | (static_cast<uint32_t>(j & 3) << 4) | (static_cast<uint32_t>(4 + (j & 3)) << 8) |
-                                   (static_cast<uint32_t>(4 + (j & 3)) << 12);  // bytes [a_j, a_j, b_j, b_j]
-              const uint32_t b0 = h2_sub(lop3_and_or(__byte_perm(wa[j >> 2], wb[j >> 2], sel), 0x00ff00ffu, kMagic), kMagic);
-              const uint32_t b1 = h2_sub(lop3_and_or(__byte_perm(wc[j >> 2], wd[j >> 2], sel), 0x00ff00ffu, kMagic), kMagic);
-              mma16816_acc(o[j][0], o[j][1], od0, od1, pa[0], pa[1], b0, b1);
+            for (int i = 0; i < 8; ++i) {
+              // dims 16g + 2i (row g) and 16g + 2i + 1 (row g+8): bytes 2i, 2i+1 of the 16-byte row chunk
+              const int w = i >> 1, b0 = 2 * (i & 1), b1 = b0 + 1;
+              const uint32_t sel0 = static_cast<uint32_t>(b0) | (static_cast<uint32_t>(b0) << 4) | (static_cast<uint32_t>(4 + b0) << 8) | (static_cast<uint32_t>(4 + b0) << 12);
+              const uint32_t sel1 = static_cast<uint32_t>(b1) | (static_cast<uint32_t>(b1) << 4) | (static_cast<uint32_t>(4 + b1) << 8) | (static_cast<uint32_t>(4 + b1) << 12);
+              mma_full(o[i][0], o[i][1], o[i][2], o[i][3], h2_sub(lop3_and_or(__byte_perm(wa[w], wb[w], sel0), 0x00ff00ffu, kMagic), kMagic),
+                       h2_sub(lop3_and_or(__byte_perm(wa[w], wb[w], sel1), 0x00ff00ffu, kMagic), kMagic),
+                       h2_sub(lop3_and_or(__byte_perm(wc[w], wd[w], sel0), 0x00ff00ffu, kMagic), kMagic),
+                       h2_sub(lop3_and_or(__byte_perm(wc[w], wd[w], sel1), 0x00ff00ffu, kMagic), kMagic), bp0, bp1);
             }
           }
         }
@@ -465,19 +454,25 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 
     // ---- per-warp partials -> shared memory (the ring is free: every stage of this CTA has been consumed) ----
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-    c_run += __shfl_xor_sync(0xffffffffu, c_run, 1);
-    c_run += __shfl_xor_sync(0xffffffffu, c_run, 2);
-    if (q4 == 0) {
-      s_m[warp][g] = m_run;
-      s_l[warp][g] = l_run;
-    }
-    float* so = s_o + (warp * kMaxG + g) * kD + 32 * q4;  // thread (g, q4) holds row g, dims 32*q4 + 16*e + j
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      so[j] = o[j][0] + c_run;
-      so[16 + j] = o[j][1] + c_run;
+    for (int m = 4; m <= 16; m <<= 1) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, m);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, m);
+      cr0 += __shfl_xor_sync(0xffffffffu, cr0, m);
+      cr1 += __shfl_xor_sync(0xffffffffu, cr1, m);
+    }
+    if (g == 0) {
+      s_m[warp][2 * q4] = m0; s_m[warp][2 * q4 + 1] = m1;
+      s_l[warp][2 * q4] = l0; s_l[warp][2 * q4 + 1] = l1;
+    }
+    {
+      float* so0 = s_o + (warp * kMaxG + 2 * q4) * kD + 16 * g;  // head 2q4, dims 16g..16g+15
+      float* so1 = so0 + kD;                                      // head 2q4+1
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        so0[2 * i] = o[i][0] + cr0; so0[2 * i + 1] = o[i][2] + cr0;
+        so1[2 * i] = o[i][1] + cr1; so1[2 * i + 1] = o[i][3] + cr1;
+      }
     }
     // new token logit: fp32 dot of the rotated, un-quantised q and k  (Template.hpp:1410-1441)
     if (split == 0) {
@@ -710,7 +705,7 @@ int decode_attention(const DecodeAttnArgs& a) {
   int nsplit = 1;
   const int ctas = gx * a.batch;
   const int slots = 148 * 4;
-  if (ctas < slots && a.timestep > 512) {
+  if (2 * ctas <= slots && a.timestep > 512) {
     nsplit = (slots + ctas - 1) / ctas;
     const int cap = (a.timestep + 255) / 256;
     if (nsplit > cap) nsplit = cap;

@@ -80,7 +80,7 @@ struct Cfg {
   static constexpr int kOffBar = kOffRow + 2 * NT * 4;
   static constexpr int kNumBars = 3 * STAGES + 1;
   static constexpr int kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr
-  static constexpr int kSmemBytes = kOffMisc + 16 + 1024;  // + alignment slack
+  static constexpr int kSmemBytes = kOffMisc + 16;
   // two co-resident CTAs per SM when both the TMEM columns (<= 256 each) and the shared memory (<= 113 KB each) allow it
   static constexpr int kCtasPerSm = (kTmemCols <= 256 && kSmemBytes <= 113 * 1024) ? 2 : 1;
 };
@@ -127,12 +127,12 @@ __device__ __forceinline__ __half epilogue_one(int32_t acc, float ws, float wsz,
 }
 
 // grid.x = tiles * split; the `split` CTAs of a cluster share one (n_tile, m_tile) and own disjoint K ranges
-template <int MODE, int NT, int STAGES>
+template <int MODE, int NT, int STAGES, bool ACC>
 __global__ void __launch_bounds__(kNumThreads, Cfg<MODE, NT, STAGES>::kCtasPerSm)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   using C = Cfg<MODE, NT, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts 1024-aligned
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* s_act = smem + C::kOffAct;
   uint8_t* s_w = smem + C::kOffW;
   uint8_t* s_s2 = smem + C::kOffS2;
@@ -349,29 +349,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       wz0 = __low2float(wz); wz1 = __high2float(wz);
     }
     const float ws0 = __low2float(ws), ws1 = __high2float(ws);
+    const int tok_end = min(NT, p.M - m0);  // tokens of this tile that exist
+    const int tok0 = epi_tid / npairs;
+    const uint32_t off0 = static_cast<uint32_t>((tok0 * kBM + 2 * pr) * 4), off_step = static_cast<uint32_t>(tstep * kBM * 4);
+    __half* optr = p.out + static_cast<size_t>(m0 + tok0) * p.N + n;
+    const size_t ostep = static_cast<size_t>(tstep) * p.N;
+    auto finish = [&](int tok, int2 acc, __half* dst) {
+      const float as = s_asc[tok], asum = s_asum[tok];
+      const __half o0 = epilogue_one<MODE>(acc.x, ws0, wz0, as, asum);
+      const __half o1 = epilogue_one<MODE>(acc.y, ws1, wz1, as, asum);
+      *reinterpret_cast<__half2*>(dst) = __halves2half2(o0, o1);
+      if constexpr (ACC) *reinterpret_cast<int2*>(p.acc_out + (dst - p.out)) = acc;
+    };
+    if (S == 1) {
 #pragma unroll 4
-    for (int tok = epi_tid / npairs; tok < NT; tok += tstep) {
-      const int m = m0 + tok;
-      const uint32_t off = static_cast<uint32_t>((tok * kBM + 2 * pr) * 4);
-      int2 acc = make_int2(0, 0);
-      if (S == 1) {
-        acc = *reinterpret_cast<const int2*>(reinterpret_cast<const uint8_t*>(s_red) + off);
-      } else {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          if (r < S) {
-            const int2 v = ld_dsmem_v2(red_peer[r] + off);
-            acc.x += v.x;
-            acc.y += v.y;
-          }
-        }
+      for (int tok = tok0, i = 0; tok < tok_end; tok += tstep, ++i) {
+        const int2 acc = *reinterpret_cast<const int2*>(reinterpret_cast<const uint8_t*>(s_red) + off0 + i * off_step);
+        finish(tok, acc, optr + i * ostep);
       }
-      if (m < p.M) {
-        const float as = s_asc[tok], asum = s_asum[tok];
-        const __half o0 = epilogue_one<MODE>(acc.x, ws0, wz0, as, asum);
-        const __half o1 = epilogue_one<MODE>(acc.y, ws1, wz1, as, asum);
-        *reinterpret_cast<__half2*>(p.out + static_cast<size_t>(m) * p.N + n) = __halves2half2(o0, o1);
-        if (p.acc_out) *reinterpret_cast<int2*>(p.acc_out + static_cast<size_t>(m) * p.N + n) = acc;
+    } else {
+      // two tokens per round: all 2*S distributed-shared-memory loads are issued before any of them is consumed
+      for (int tok = tok0, i = 0; tok < tok_end; tok += 2 * tstep, i += 2) {
+        int2 v[2][8];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r < S) v[e][r] = ld_dsmem_v2(red_peer[r] + off0 + (i + e) * off_step);  // over-read of the 2nd token stays inside s_red
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int2 acc = make_int2(0, 0);
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r < S) { acc.x += v[e][r].x; acc.y += v[e][r].y; }
+          if (tok + e * tstep < tok_end) finish(tok + e * tstep, acc, optr + (i + e) * ostep);
+        }
       }
     }
     if (epi_tid == 0) QS_PROF(11);
@@ -481,12 +493,12 @@ int launch_gemm(const GemmArgs& a) {
   rc = (MODE == kModeW8) ? make_tmap_u8(&tm_w, a.weight, a.N, a.K, kBM) : make_tmap_w4(&tm_w, a.weight, a.N, a.K);
   if (rc) return rc;
 
-  auto kern = gemm_kernel<MODE, NT, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  auto kern = a.acc_out ? gemm_kernel<MODE, NT, STAGES, true> : gemm_kernel<MODE, NT, STAGES, false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[a.acc_out ? 1 : 0]) {
     rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "cudaFuncSetAttribute(gemm smem)");
     if (rc) return rc;
-    attr_set = true;
+    attr_set[a.acc_out ? 1 : 0] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles * p.split);
