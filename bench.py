@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-fused", action="store_true", help="use exactly the reference op sequence (no fused add+norm / silu+quant extensions)")
     ap.add_argument("--kernel-reps", type=int, default=5)
     return ap.parse_args()
 
@@ -217,7 +218,7 @@ def main():
     backend.set_pdl(not args.no_pdl)
     cfg = MODELS[args.model]
     tp = world if args.model in ("qwen1.5-72b",) and world > 1 else 1
-    run = DecodeRunner(args.model, args.precision, args.batch, args.ctx, dev, tp_rank=rank if tp > 1 else 0, tp_size=tp, seed=rank, layers=args.layers)
+    run = DecodeRunner(args.model, args.precision, args.batch, args.ctx, dev, tp_rank=rank if tp > 1 else 0, tp_size=tp, seed=rank, layers=args.layers, fused=not args.no_fused)
     hbm_gbs, peak_src = peaks()
 
     # ---- pinned host buffers for the end-to-end leg ------------------------------------------------------
@@ -304,7 +305,7 @@ def main():
                    "precision": args.precision, "batch": args.batch, "ctx": args.ctx, "layers": run.L,
                    "parallelism": (f"dp{world}" if tp == 1 else f"tp{tp}"),
                    "l2": f"per-step working set {step_bytes / 1e9:.2f} GB (weights + KV pages + lm_head) >> 126 MB L2: inputs larger than L2, no flush needed",
-                   "pdl": not args.no_pdl},
+                   "pdl": not args.no_pdl, "fused_small_ops": not args.no_fused},
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": args.batch * 8 * replicas, "d2h_bytes_per_step": args.batch * 8 * replicas,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": run.launches_per_step * args.steps,

@@ -141,6 +141,17 @@ QS_API int qs_gelu_fast(void* out, const void* input, int tokens, int d, void* s
 QS_API int qs_dequant_silu_and_mul_quant(int8_t* out, const int32_t* input, float scale_gate, float scale_up, float scale_out,
                                   float* scale_out_vec, float* tmp, int tokens, int d, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused extensions (NOT part of the reference surface; bit-identical to the op sequences they replace).
+ * Used by qserve_b200/decode.py to cut the launch count of the decode step.
+ * --------------------------------------------------------------------------------------------------------- */
+/* hidden_out = half(x + delta)   [the torch `residual + out_buf` of llama_w4a8_unpad.py:348,360]
+ * followed by rms_norm_general[_fuse_sum](out, hidden_out, weight, input_sum | NULL, scaling, epsilon, per_token=1)      */
+QS_API int qs_add_rms_norm_general(int8_t* out, void* hidden_out, const void* x, const void* delta, const void* weight, void* input_sum,
+                                   void* scaling, float epsilon, int tokens, int hidden, void* stream);
+/* silu_and_mul(input [tokens, 2d]) followed by invoke_quant[_fuse_sum](out, act, input_sum | NULL, scale)                 */
+QS_API int qs_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int tokens, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

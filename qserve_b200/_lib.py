@@ -37,6 +37,8 @@ SIGNATURES = {
     "qs_invoke_dequant_add_residual": (c_int, [_P, _P, _P, _P, _F, _I, _I, _P]),
     "qs_invoke_dequant": (c_int, [_P, _P, _F, _I, _I, _I, _I, _P]),
     "qs_silu_and_mul": (c_int, [_P, _P, _I, _I, _P]),
+    "qs_silu_and_mul_quant": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "qs_add_rms_norm_general": (c_int, [_P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _P]),
     "qs_gelu_new": (c_int, [_P, _P, _I, _I, _P]),
     "qs_gelu_fast": (c_int, [_P, _P, _I, _I, _P]),
     "qs_dequant_silu_and_mul_quant": (c_int, [_P, _P, _F, _F, _F, _P, _P, _I, _I, _P]),

@@ -354,3 +354,30 @@ def invoke_dequant_silu_and_mul_quant(out, input, scale_gate: float, scale_up: f
     else:
         check(lib.qs_dequant_silu_and_mul_quant(out.data_ptr(), input.data_ptr(), float(scale_gate), float(scale_up), float(scale_out), None, None,
                                                 tokens, d, _stream(input)))
+
+
+# --------------------------------------------------------------------------------------------------
+# fused extensions (not part of the reference surface; bit-identical to the op sequences they replace)
+# --------------------------------------------------------------------------------------------------
+
+
+def add_rms_norm_general(out, hidden_out, x, delta, weight, input_sum: Optional[torch.Tensor], scaling, epsilon: float) -> None:
+    """hidden_out = x + delta (fp16, as torch computes `residual + out_buf`), then rms_norm_general[_fuse_sum](out, hidden_out, ...)."""
+    _cuda(x, "x"); _half_only(x, "add_rms_norm_general"); _half_only(delta, "add_rms_norm_general")
+    if _noop(x):
+        return
+    tokens, hidden = _rows(x)
+    check(lib.qs_add_rms_norm_general(out.data_ptr(), hidden_out.data_ptr(), x.data_ptr(), delta.data_ptr(), weight.data_ptr(),
+                                      input_sum.data_ptr() if input_sum is not None else None, scaling.data_ptr(), float(epsilon), tokens, hidden,
+                                      _stream(x)))
+
+
+def silu_and_mul_quant(out, input, input_sum: Optional[torch.Tensor], scale) -> None:
+    """silu_and_mul(input) followed by invoke_quant[_fuse_sum]; the fp16 activation never leaves the SM."""
+    _cuda(input, "input"); _half_only(input, "silu_and_mul_quant")
+    if _noop(input):
+        return
+    d = input.size(-1) // 2
+    tokens = input.numel() // input.size(-1)
+    check(lib.qs_silu_and_mul_quant(out.data_ptr(), input.data_ptr(), input_sum.data_ptr() if input_sum is not None else None, scale.data_ptr(),
+                                    tokens, d, _stream(input)))

@@ -178,6 +178,17 @@ int qs_invoke_dequant(void* out, const int32_t* input, float scale, int tokens, 
   return dequant(out, input, scale, tokens, hidden, input_stride, out_stride, stream);
 }
 
+int qs_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int tokens, int d, void* stream) {
+  QS_REQUIRE(out && input && scale, "silu_and_mul_quant: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input), "silu_and_mul_quant: tensors must be 16-byte aligned");
+  return silu_and_mul_quant(out, input, input_sum, scale, tokens, d, stream);
+}
+int qs_add_rms_norm_general(int8_t* out, void* hidden_out, const void* x, const void* delta, const void* weight, void* input_sum, void* scaling,
+                            float epsilon, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && hidden_out && x && delta && weight && scaling, "add_rms_norm_general: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(hidden_out) && aligned16(x) && aligned16(delta) && aligned16(weight), "add_rms_norm_general: tensors must be 16-byte aligned");
+  return add_layernorm_quant(out, hidden_out, x, delta, weight, input_sum, scaling, epsilon, tokens, hidden, stream);
+}
 int qs_silu_and_mul(void* out, const void* input, int tokens, int d, void* stream) {
   QS_REQUIRE(out && input, "silu_and_mul: null tensor");
   QS_REQUIRE(aligned16(out) && aligned16(input), "silu_and_mul: tensors must be 16-byte aligned");

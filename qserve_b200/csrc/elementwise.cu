@@ -155,6 +155,157 @@ __global__ void __launch_bounds__(kThreads) layernorm_quant_kernel(int8_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused extensions (bit-identical to the unfused op sequences they replace; tests/test_gpu_fused.py)
+//   add_layernorm_quant : hidden = half(x + delta)  [torch `residual + out_buf`, llama_w4a8_unpad.py:348,360]  -> N1
+//   silu_mul_quant      : act = silu_and_mul(in)    [activation.py:24-29]                                      -> Q1
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = kThreads;  // same thread count and loop order as the unfused kernels -> bit-identical sums
+
+__global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8_t* __restrict__ out, __half* __restrict__ hidden_out,
+                                                                           const __half* __restrict__ x, const __half* __restrict__ delta,
+                                                                           const __half* __restrict__ gamma, __half* __restrict__ input_sum,
+                                                                           __half* __restrict__ scaling, float eps, int H, int ref_block) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __half* sx = reinterpret_cast<__half*>(sm);
+  __half* sy = sx + H;
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  {
+    const uint4* a = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
+    const uint4* b = reinterpret_cast<const uint4*>(delta + static_cast<size_t>(row) * H);
+    uint4* ho = reinterpret_cast<uint4*>(hidden_out + static_cast<size_t>(row) * H);
+    for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+      const uint4 va = __ldg(a + i), vb = __ldg(b + i);
+      uint4 vo;
+      const __half2* ha = reinterpret_cast<const __half2*>(&va);
+      const __half2* hb = reinterpret_cast<const __half2*>(&vb);
+      __half2* ho2 = reinterpret_cast<__half2*>(&vo);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // torch half add: float(a) + float(b), rounded once to fp16
+        const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
+        ho2[j] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+      }
+      reinterpret_cast<uint4*>(sx)[i] = vo;
+      ho[i] = vo;
+    }
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      s += f.x + f.y;
+    }
+  }
+  const float mean = __fdiv_rn(block_reduce(s, red, OpSum(), 0.f), static_cast<float>(H));
+  float vs = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      const float a = f.x - mean, b = f.y - mean;
+      vs += a * a + b * b;
+    }
+  }
+  const float var = block_reduce(vs, red, OpSum(), 0.f);
+  const float rstd = __frsqrt_rn(__fadd_rn(__fdiv_rn(var, static_cast<float>(H)), eps));
+  float amax = __half2float(__float2half_rn(1e-6f));
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    const __half* gh = reinterpret_cast<const __half*>(&g);
+    uint4 yv;
+    __half* yh = reinterpret_cast<__half*>(&yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = __fmul_rn(__fmul_rn(__fsub_rn(__half2float(h[j]), mean), rstd), __half2float(gh[j]));
+      yh[j] = __float2half_rn(y);
+      amax = fmaxf(amax, fabsf(__half2float(yh[j])));
+    }
+    if (input_sum) reinterpret_cast<uint4*>(sy)[i] = yv;
+  }
+  amax = block_reduce(amax, red, OpMax(), 0.f);
+  if (input_sum) {
+    float part = 0.f;
+    for (int t = threadIdx.x; t < ref_block; t += blockDim.x) {
+      __half acc = __float2half_rn(0.f);
+      for (int i = t; i < H; i += ref_block) acc = __hadd(acc, sy[i]);
+      part += __half2float(acc);
+    }
+    const float total = block_reduce(part, red, OpSum(), 0.f);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+  }
+  if (threadIdx.x == 0) scaling[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+  const float qs_ = __fdiv_rn(127.f, amax);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    const __half* gh = reinterpret_cast<const __half*>(&g);
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = __fmul_rn(__fmul_rn(__fsub_rn(__half2float(h[j]), mean), rstd), __half2float(gh[j]));
+    store_q8(out + static_cast<size_t>(row) * H, i, y, qs_);
+  }
+}
+
+__device__ __forceinline__ __half silu_h_fused(__half x) {
+  const float f = __half2float(x);
+  return __float2half_rn(__fdiv_rn(f, __fadd_rn(1.0f, expf(-f))));
+}
+
+__global__ void __launch_bounds__(kFusedThreads) silu_mul_quant_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
+                                                                      __half* __restrict__ input_sum, __half* __restrict__ scale, int d) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __half* sa = reinterpret_cast<__half*>(sm);  // activation row (fp16), d elements
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  pdl_wait();
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d);
+  const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d);
+  float amax = 0.f, s = 0.f;
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
+    const uint4 x = __ldg(gx + i), y = __ldg(gy + i);
+    const __half* xh = reinterpret_cast<const __half*>(&x);
+    const __half* yh = reinterpret_cast<const __half*>(&y);
+    uint4 o;
+    __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      oh[j] = __hmul(silu_h_fused(xh[j]), yh[j]);
+      const float f = __half2float(oh[j]);
+      s += f;
+      amax = fmaxf(amax, fabsf(f));
+    }
+    reinterpret_cast<uint4*>(sa)[i] = o;
+  }
+  amax = block_reduce(amax, red, OpMax(), 0.f);  // (the barriers inside also publish sa)
+  if (input_sum) {
+    const float total = block_reduce(s, red, OpSum(), 0.f);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+  }
+  if (threadIdx.x == 0) scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+  const float qs_ = __fdiv_rn(127.f, amax);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
+    const uint4 v = reinterpret_cast<const uint4*>(sa)[i];
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __half2float(h[j]);
+    store_q8(out + static_cast<size_t>(row) * d, i, x, qs_);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Q1: invoke_quant / invoke_quant_fuse_sum (per-token)   fused_kernels.cu:52-137
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) quant_per_token_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
@@ -482,8 +633,28 @@ int dequant_silu_and_mul_quant(void* out_q, const void* in_i32, float scale_gate
                 static_cast<float*>(scale_out_vec), static_cast<float*>(tmp));
 }
 
-int silu_and_mul_quant(void*, const void*, void*, void*, int, int, void*) {
-  return set_error(QS_ERR_UNSUPPORTED, "silu_and_mul_quant: not built in this revision");
+int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int d, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(d > 0 && d % 8 == 0, "silu_and_mul_quant: d=%d must be a positive multiple of 8", d);
+  const size_t smem = static_cast<size_t>(d) * 2;
+  int rc = ensure_smem(silu_mul_quant_kernel, smem, "silu_and_mul_quant");
+  if (rc) return rc;
+  return launch(silu_mul_quant_kernel, dim3(tokens), dim3(kFusedThreads), smem, stream, "silu_and_mul_quant", static_cast<int8_t*>(out_q),
+                static_cast<const __half*>(in), static_cast<__half*>(input_sum), static_cast<__half*>(scale), d);
+}
+
+int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void* delta, const void* gamma, void* input_sum, void* scaling,
+                        float eps, int tokens, int hidden, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "add_rms_norm_general: hidden=%d must be a positive multiple of 8", hidden);
+  const size_t smem = static_cast<size_t>(hidden) * 2 * (input_sum ? 2 : 1);
+  int rc = ensure_smem(add_layernorm_quant_kernel, smem, "add_rms_norm_general");
+  if (rc) return rc;
+  int ref_block = hidden < 1024 ? hidden : 1024;
+  ref_block = 32 * ((ref_block + 31) / 32);
+  return launch(add_layernorm_quant_kernel, dim3(tokens), dim3(kFusedThreads), smem, stream, "add_rms_norm_general", static_cast<int8_t*>(out_q),
+                static_cast<__half*>(hidden_out), static_cast<const __half*>(x), static_cast<const __half*>(delta),
+                static_cast<const __half*>(gamma), static_cast<__half*>(input_sum), static_cast<__half*>(scaling), eps, hidden, ref_block);
 }
 
 }  // namespace qs

@@ -39,6 +39,8 @@ int quant_per_token(void* out_q, const void* in, void* input_sum, void* scale, i
 int quant_scalar(void* out_q, const void* in, float scale, int tokens, int hidden, void* stream);
 int silu_and_mul(void* out, const void* in, int tokens, int d, void* stream);
 int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int d, void* stream);
+int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void* delta, const void* gamma, void* input_sum, void* scaling, float eps,
+                        int tokens, int hidden, void* stream);
 int gelu(void* out, const void* in, int tokens, int d, int fast, void* stream);
 int dequant_add_residual(void* out, const void* in_i32, const void* residual, const void* scale_vec, float scale, int tokens, int hidden,
                          void* stream);

@@ -26,6 +26,7 @@ import qserve_backend.layernorm_ops as layernorm_ops
 import qserve_backend.qgemm_w4a8_per_chn as qgemm_chn
 import qserve_backend.qgemm_w4a8_per_group as qgemm_grp
 import qserve_backend.qgemm_w8a8 as qgemm_w8
+from qserve_b200 import backend as _ext
 
 
 @dataclass(frozen=True)
@@ -94,12 +95,13 @@ class _Linear:
 class DecodeRunner:
     def __init__(self, model: str = "llama-3-8b", precision: str = "w4a8kv4", batch: int = 64, ctx: int = 1024,
                  device: Optional[torch.device] = None, tp_rank: int = 0, tp_size: int = 1, seed: int = 0, layers: Optional[int] = None,
-                 process_group=None):
+                 process_group=None, fused: bool = True):
         assert precision in PRECISIONS, precision
         self.cfg = cfg = MODELS[model]
         self.precision, self.batch, self.ctx = precision, batch, ctx
         self.dev = dev = device or torch.device("cuda", torch.cuda.current_device())
         self.tp_rank, self.tp_size, self.pg = tp_rank, tp_size, process_group
+        self.fused = fused  # fused residual+norm+quant and silu*mul+quant extensions (bit-identical to the reference op sequence)
         self.L = layers if layers is not None else cfg.layers
         gen = torch.Generator(device=dev)
         gen.manual_seed(seed + 1000 * tp_rank)
@@ -190,21 +192,29 @@ class DecodeRunner:
 
     def forward(self, tokens: torch.Tensor) -> torch.Tensor:
         """One decode step for `batch` sequences; returns the greedy next tokens [batch] (device)."""
+        return self._forward_fused(tokens) if self.fused else self._forward_reference(tokens)
+
+    def _attention(self, li):
         cfg, D = self.cfg, self.cfg.head_dim
+        q, k, v = self.qkv_buf.split([self.q_size, self.kv_size, self.kv_size], dim=-1)  # :245-252
+        q = q.reshape(q.size(0), self.Hq, D)
+        k = k.reshape(k.size(0), self.Hkv, D)
+        v = v.reshape(v.size(0), self.Hkv, D)
+        attn = fused_attention.single_query_attention(
+            q, k, v, self.block_tables[li], self.context_lens, None, min(8192, cfg.max_pos), 64, self.size_per_token,
+            self.max_seq_len, D, cfg.rope_theta, True, self.kv_bits == 4, True)  # :265-281
+        return attn.reshape(q.size(0), -1)
+
+    def _forward_reference(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Exactly the reference's op sequence (LlamaDecoderLayer.forward, llama_w4a8_unpad.py:330-361)."""
+        cfg = self.cfg
         n = 0
         hidden = self.embed[tokens]  # LlamaModel.forward (:401-404)
         for li, ly in enumerate(self.layers):
             residual = hidden
             self._norm_quant(hidden, ly["ln1"])
             ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
-            q, k, v = self.qkv_buf.split([self.q_size, self.kv_size, self.kv_size], dim=-1)  # :245-252
-            q = q.reshape(q.size(0), self.Hq, D)
-            k = k.reshape(k.size(0), self.Hkv, D)
-            v = v.reshape(v.size(0), self.Hkv, D)
-            attn = fused_attention.single_query_attention(
-                q, k, v, self.block_tables[li], self.context_lens, None, min(8192, cfg.max_pos), 64, self.size_per_token,
-                self.max_seq_len, D, cfg.rope_theta, True, self.kv_bits == 4, True)  # :265-281
-            attn = attn.reshape(q.size(0), -1)
+            attn = self._attention(li)
             self._quant(self.q_attn, attn)
             ly["o"](self.q_attn, self.q_scale, self.q_sum, self.out_buf)
             self._allreduce(self.out_buf)
@@ -221,6 +231,41 @@ class DecodeRunner:
         out = torch.empty_like(hidden)
         layernorm_ops.rms_norm(out, hidden, self.norm_w, cfg.eps, False)  # final norm (:408)
         logits = torch.nn.functional.linear(out, self.lm_head)           # fp16 lm_head (:474-476)
+        self.launches_per_step = n + 1
+        return torch.argmax(logits, dim=-1)
+
+    def _forward_fused(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Same arithmetic, three launches fewer per layer: the two torch residual adds are folded into the following norm
+        (`add_rms_norm_general`) and silu_and_mul into the following per-token quant (`silu_and_mul_quant`)."""
+        cfg = self.cfg
+        qsum = self.q_sum if self.act_sum else None
+        n = 0
+        hidden = self.embed[tokens]
+        nxt = torch.empty_like(hidden)
+        self._norm_quant(hidden, self.layers[0]["ln1"])
+        n += 1
+        for li, ly in enumerate(self.layers):
+            ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
+            attn = self._attention(li)
+            self._quant(self.q_attn, attn)
+            ly["o"](self.q_attn, self.q_scale, self.q_sum, self.out_buf)
+            self._allreduce(self.out_buf)
+            _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, ly["ln2"], qsum, self.q_scale, cfg.eps)
+            hidden, nxt = nxt, hidden
+            ly["gate_up"](self.q_hidden, self.q_scale, self.q_sum, self.gate_up_buf)
+            _ext.silu_and_mul_quant(self.q_mlp, self.gate_up_buf, qsum, self.q_scale)
+            ly["down"](self.q_mlp, self.q_scale, self.q_sum, self.out_buf)
+            self._allreduce(self.out_buf)
+            n += 8
+            if li + 1 < len(self.layers):
+                _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, self.layers[li + 1]["ln1"], qsum, self.q_scale, cfg.eps)
+                hidden, nxt = nxt, hidden
+                n += 1
+            else:
+                hidden = hidden + self.out_buf
+        out = torch.empty_like(hidden)
+        layernorm_ops.rms_norm(out, hidden, self.norm_w, cfg.eps, False)
+        logits = torch.nn.functional.linear(out, self.lm_head)
         self.launches_per_step = n + 1
         return torch.argmax(logits, dim=-1)
 

@@ -76,7 +76,12 @@ def attention():
         q, k, v = (rng.standard_normal(s).astype(np.float16) for s in ((B, Hq, D), (B, Hkv, D), (B, Hkv, D)))
         kd, vd = t(kp.data), t(vp.data)
         table = torch.from_numpy(np.stack([kd.data_ptr() + bt * kp.pb, vd.data_ptr() + bt * vp.pb], axis=1)).to(dev)
-        out = fa.single_query_attention(t(q), t(k), t(v), table, torch.tensor(lens, dtype=torch.int32, device=dev), None, 8192, 64,
+        # the reference takes the row stride of q, k AND v from q.stride(0) (fused_attention.cpp:215): they must be views of
+        # one packed qkv buffer, exactly as llama_w4a8_unpad.py:245-252 passes them
+        qkv_d = torch.from_numpy(np.concatenate([q.reshape(B, -1), k.reshape(B, -1), v.reshape(B, -1)], axis=1)).to(dev)
+        qd, kd_, vd_ = qkv_d.split([Hq * D, Hkv * D, Hkv * D], dim=-1)
+        out = fa.single_query_attention(qd.reshape(B, Hq, D), kd_.reshape(B, Hkv, D), vd_.reshape(B, Hkv, D), table,
+                                        torch.tensor(lens, dtype=torch.int32, device=dev), None, 8192, 64,
                                         Hkv * D * bits // 8, max(lens), D, 10000.0, True, bits == 4, True)
         torch.cuda.synchronize()
         np.savez_compressed(os.path.join(OUT, f"ref_decode_attn_kv{bits}.npz"), q=q, k=k, v=v, kpool=kp.data, vpool=vp.data, bt=bt, lens=np.array(lens),
