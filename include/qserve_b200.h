@@ -77,6 +77,9 @@ QS_API size_t qs_gemm_workspace_bytes(void);
 QS_API int qs_gemm_force_split(int split);
 /* profiling hook: device buffer of 16 x uint64 per CTA receiving %globaltimer stamps of the GEMM phases; NULL disables */
 QS_API int qs_gemm_set_profile_buffer(void* dev_buffer);
+/* step tracing: u64 buffer [0] = record count (zero it), then `capacity_records` x (kernel_id << 8 | phase, %globaltimer);
+ * block 0 of every kernel logs entry (0), dependency resolved (1) and exit (2); NULL disables (tools/step_timeline.py) */
+QS_API int qs_set_trace_buffer(void* dev_buffer, unsigned capacity_records);
 
 /* ---------------------------------------------------------------------------------------------------------
  * qserve_backend.fused_attention.single_query_attention         kernels/csrc/fused_attention/fused_attention.cpp:150-240
@@ -149,6 +152,14 @@ QS_API int qs_dequant_silu_and_mul_quant(int8_t* out, const int32_t* input, floa
  * followed by rms_norm_general[_fuse_sum](out, hidden_out, weight, input_sum | NULL, scaling, epsilon, per_token=1)      */
 QS_API int qs_add_rms_norm_general(int8_t* out, void* hidden_out, const void* x, const void* delta, const void* weight, void* input_sum,
                                    void* scaling, float epsilon, int tokens, int hidden, void* stream);
+/* single_query_attention followed by invoke_quant[_fuse_sum] of the [B, Hq*D] result: out_q int8 [B, Hq*D], out_scale fp16 [B],
+ * out_sum fp16 [B] or NULL.  The CTAs of one token form a thread-block cluster and exchange the row amax / sum through
+ * distributed shared memory.  Returns QS_ERR_UNSUPPORTED when a token needs more than 8 CTAs (callers then run the two ops). */
+QS_API int qs_single_query_attention_quant(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride, int64_t v_stride,
+                                           const int64_t* kv_pointers, const int32_t* length_per_sample, int8_t* out_q, void* out_scale,
+                                           void* out_sum, int batch, int num_heads, int num_kv_heads, int head_dim, int max_blocks_per_seq,
+                                           int memory_max_seqlen, int tokens_per_block, int size_per_token, int timestep,
+                                           int rotary_embedding_dim, float rotary_base, int int4_kv_cache, int kv_cache_with_zeros, void* stream);
 /* silu_and_mul(input [tokens, 2d]) followed by invoke_quant[_fuse_sum](out, act, input_sum | NULL, scale)                 */
 QS_API int qs_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int tokens, int d, void* stream);
 

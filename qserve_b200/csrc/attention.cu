@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(kAttnThreadsV2, 4)
 decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restrict__ k_in, const __half* __restrict__ v_in, long long q_stride,
                         long long k_stride, long long v_stride, const long long* __restrict__ kv_pointers, const int* __restrict__ lengths,
                         __half* __restrict__ out, int num_heads, int num_kv_heads, int max_blocks, PageGeom pg, float rotary_base, int rotary_dim,
-                        int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt) {
+                        int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt, int8_t* __restrict__ q_out,
+                        __half* __restrict__ q_scale, __half* __restrict__ q_sum) {
   using SL = StageLayout<BITS>;
   constexpr int R = SL::kStages;
   const int G = num_heads / num_kv_heads;
@@ -178,7 +179,9 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
     }
     fence_barrier_init();
   }
+  qs_trace(QS_K_ATTN, 0);
   pdl_wait();
+  qs_trace(QS_K_ATTN, 1);
   if (threadIdx.x == 0) pdl_launch_dependents();
 
   const int tlen = (lengths ? lengths[b] : timestep) - 1;  // tokens already in the cache (Template.hpp:901)
@@ -493,38 +496,102 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 
   // ---------------- merge the warps (and the un-quantised new token); one output dim per thread ----------------
   const bool owner = (split == 0);
+  __half hq[kMaxG];      // fused-quant mode: this thread's outputs, kept for the second pass
+  float amax_l = 0.f;
+  long long sum_l = 0;
   if (threadIdx.x < kD) {
     const int d = threadIdx.x;
     const int nparts = kWarps + (owner ? 1 : 0);
     float* part = nullptr;
     if (nsplit > 1) part = ws_part + ((static_cast<size_t>(b) * num_heads + h0) * nsplit + split) * (kD + 2);
-    for (int r = 0; r < Gc; ++r) {
-      float M = -CUDART_INF_F;
-      for (int w = 0; w < nparts; ++w) M = fmaxf(M, s_m[w][r]);
-      float L = 0.f, acc = 0.f;
-      for (int w = 0; w < kWarps; ++w) {
-        const float e = (s_m[w][r] == -CUDART_INF_F) ? 0.f : exp2f(s_m[w][r] - M);
-        L += s_l[w][r] * e;
-        acc += s_o[(w * kMaxG + r) * kD + d] * e;
-      }
-      if (owner) {
-        const float e = exp2f(s_m[kWarps][r] - M);
-        L += e;
-        acc += e * __half2float(s_v[d]);
-      }
-      if (nsplit == 1) {
-        // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
-        out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
-      } else {
-        float* pr = part + static_cast<size_t>(r) * nsplit * (kD + 2);
-        pr[d] = acc;
-        if (d == 0) {
-          pr[kD] = M;
-          pr[kD + 1] = L;
+#pragma unroll
+    for (int r = 0; r < kMaxG; ++r) {
+      if (r < Gc) {
+        float M = -CUDART_INF_F;
+        for (int w = 0; w < nparts; ++w) M = fmaxf(M, s_m[w][r]);
+        float L = 0.f, acc = 0.f;
+        for (int w = 0; w < kWarps; ++w) {
+          const float e = (s_m[w][r] == -CUDART_INF_F) ? 0.f : exp2f(s_m[w][r] - M);
+          L += s_l[w][r] * e;
+          acc += s_o[(w * kMaxG + r) * kD + d] * e;
+        }
+        if (owner) {
+          const float e = exp2f(s_m[kWarps][r] - M);
+          L += e;
+          acc += e * __half2float(s_v[d]);
+        }
+        if (nsplit == 1) {
+          // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
+          const __half h = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
+          if (q_out == nullptr) {
+            out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = h;
+          } else {
+            hq[r] = h;
+            const float f = __half2float(h);
+            amax_l = fmaxf(amax_l, fabsf(f));
+            sum_l += __float2ll_rn(f * 16777216.f);
+          }
+        } else {
+          float* pr = part + static_cast<size_t>(r) * nsplit * (kD + 2);
+          pr[d] = acc;
+          if (d == 0) {
+            pr[kD] = M;
+            pr[kD + 1] = L;
+          }
         }
       }
     }
   }
+  if (q_out != nullptr) {
+    // ---- fused per-token INT8 quantisation of the attention output (invoke_quant[_fuse_sum], fused_kernels.cu:92-137):
+    //      the token row spans all CTAs of the cluster (one per kv head); amax / exact sum exchanged through DSMEM ----
+    __shared__ float s_red_f[8];
+    __shared__ long long s_red_l[8];
+    __shared__ __align__(16) long long s_part[2];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      amax_l = fmaxf(amax_l, __shfl_xor_sync(0xffffffffu, amax_l, m));
+      sum_l += __shfl_xor_sync(0xffffffffu, sum_l, m);
+    }
+    if (lane == 0) { s_red_f[warp] = amax_l; s_red_l[warp] = sum_l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f;
+      long long t = 0;
+      for (int w = 0; w < kAttnThreadsV2 / 32; ++w) { a = fmaxf(a, s_red_f[w]); t += s_red_l[w]; }
+      s_part[0] = __float_as_int(a);
+      s_part[1] = t;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(s_part));
+    float amax = 0.f;
+    long long total = 0;
+    for (int r = 0; r < static_cast<int>(gridDim.x); ++r) {
+      uint32_t peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(base), "r"(r));
+      long long a, t;
+      asm volatile("ld.shared::cluster.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(t) : "r"(peer) : "memory");
+      amax = fmaxf(amax, __int_as_float(static_cast<int>(a)));
+      total += t;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      q_scale[b] = __float2half_rn(__fdiv_rn(amax, 127.f));
+      if (q_sum) q_sum[b] = __float2half_rn(__ll2float_rn(total) * (1.f / 16777216.f));
+    }
+    if (threadIdx.x < kD) {
+      const float qs_ = __fdiv_rn(127.f, amax);
+#pragma unroll
+      for (int r = 0; r < kMaxG; ++r) {
+        if (r < Gc) {
+          int32_t c;
+          asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(c) : "f"(__fmul_rn(__half2float(hq[r]), qs_)));
+          q_out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + threadIdx.x] = static_cast<int8_t>(c);
+        }
+      }
+    }
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+  }
+  qs_trace(QS_K_ATTN, 2);
   if (nsplit > 1) {
     __threadfence();
     __syncthreads();
@@ -685,6 +752,8 @@ size_t attention_workspace_bytes(int batch, int num_heads, int head_dim, int max
   return kAttnCounterBytes + static_cast<size_t>(batch) * num_heads * max_splits * (head_dim + 2) * sizeof(float);
 }
 
+int attention_trace_install(void* buf, unsigned cap) { return qs_trace_install(buf, cap); }
+
 int decode_attention(const DecodeAttnArgs& a) {
   if (a.batch == 0) return QS_OK;
   QS_REQUIRE(a.head_dim == kD, "single_query_attention: head_dim=%d, only 128 is supported (as in the reference)", a.head_dim);
@@ -722,6 +791,12 @@ int decode_attention(const DecodeAttnArgs& a) {
       part = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + kAttnCounterBytes);
     }
   }
+  const bool fused_quant = a.q_out != nullptr;
+  if (fused_quant) {
+    if (gx > 8) return set_error(QS_ERR_UNSUPPORTED, "single_query_attention_quant: %d CTAs per token exceed the portable cluster size (8)", gx);
+    QS_REQUIRE(a.q_scale != nullptr, "single_query_attention_quant: q_scale is null");
+    nsplit = 1;
+  }
   dim3 grid(gx, a.batch, nsplit);
   auto run = [&](auto kern, size_t smem) {
     static bool attr_done[2] = {false, false};
@@ -731,10 +806,24 @@ int decode_attention(const DecodeAttnArgs& a) {
       if (rc) return rc;
       attr_done[which] = true;
     }
-    return launch_pdl(kern, grid, dim3(kAttnThreadsV2), smem, a.stream, "single_query_attention", static_cast<const __half*>(a.q),
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kAttnThreadsV2);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(a.stream);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = fused_quant ? gx : 1;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return check_cuda(cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(a.q),
                       static_cast<const __half*>(a.k), static_cast<const __half*>(a.v), a.q_stride, a.k_stride, a.v_stride, a.kv_pointers, a.lengths,
                       static_cast<__half*>(a.out), a.num_heads, a.num_kv_heads, a.max_blocks, pg, a.rotary_base, a.rotary_dim, a.timestep, nsplit,
-                      part, cnt);
+                      part, cnt, static_cast<int8_t*>(a.q_out), static_cast<__half*>(a.q_scale), static_cast<__half*>(a.q_sum)), "single_query_attention");
   };
   QS_REQUIRE((a.timestep + 63) / 64 + 1 <= kMaxBlocksSmem, "single_query_attention: context of %d tokens exceeds the %d pages staged in shared memory", a.timestep, kMaxBlocksSmem);
   QS_REQUIRE(a.tokens_per_block == kPageTokens, "single_query_attention: tokens_per_block=%d, only 64 is supported (cache_engine block_size)", a.tokens_per_block);

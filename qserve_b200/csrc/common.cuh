@@ -51,6 +51,31 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
+// step tracing (tools/step_timeline.py): block (0,0,0) of every kernel logs %globaltimer at entry, after the PDL wait and
+// at exit into a device buffer [0] = record count, then records of 2 x u64: (kernel_id << 8 | phase), time.  Off by default.
+// ---------------------------------------------------------------------------------------------
+static __device__ unsigned long long* g_qs_trace = nullptr;
+static __device__ unsigned int g_qs_trace_cap = 0;
+__device__ __forceinline__ void qs_trace(unsigned kernel_id, unsigned phase) {
+  if (g_qs_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    const unsigned long long i = atomicAdd(g_qs_trace, 1ull);
+    if (i < g_qs_trace_cap) {
+      g_qs_trace[1 + 2 * i] = (static_cast<unsigned long long>(kernel_id) << 8) | phase;
+      g_qs_trace[2 + 2 * i] = t;
+    }
+  }
+}
+static inline int qs_trace_install(void* buf, unsigned cap) {
+  unsigned long long* p = static_cast<unsigned long long*>(buf);
+  if (cudaMemcpyToSymbol(g_qs_trace, &p, sizeof(p)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_qs_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return -1;
+  return 0;
+}
+enum : unsigned { QS_K_GEMM = 1, QS_K_ATTN = 2, QS_K_NORM = 3, QS_K_QUANT = 4, QS_K_SILU = 5, QS_K_RMS = 6, QS_K_ADDNORM = 7, QS_K_SILUQ = 8, QS_K_PREFILL = 9 };
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -40,6 +40,24 @@ __device__ __forceinline__ float block_reduce(float v, float* red, Op op, float 
   return r;
 }
 
+// Exact, order-independent row sums of fp16 values: every fp16 is an integer multiple of 2^-24, so a row of up to 2^14
+// values sums exactly in int64 fixed point; the result is rounded ONCE to fp32 (then to fp16 by the caller).  Bit-identical
+// for every thread count / decomposition and to the oracle's float64 sum.
+__device__ __forceinline__ long long fx_of_half(float f) { return __float2ll_rn(f * 16777216.f); }
+__device__ __forceinline__ float fx_to_float(long long v) { return __ll2float_rn(v) * (1.f / 16777216.f); }
+__device__ __forceinline__ long long block_sum_ll(long long v, long long* red) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  long long r = (l < (blockDim.x >> 5)) ? red[l] : 0ll;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+  return r;
+}
+
 __device__ __forceinline__ void load_row_to_smem(__half* dst, const __half* src, int H) {
   // H % 8 == 0 guaranteed by the host wrapper
   const uint4* s = reinterpret_cast<const uint4*>(src);
@@ -70,8 +88,11 @@ __global__ void __launch_bounds__(kThreads) layernorm_quant_kernel(int8_t* __res
   __half* sx = reinterpret_cast<__half*>(sm);  // x row
   __half* sy = sx + H;                         // half(y) row (only for the fused sum)
   __shared__ float red[32];
+  __shared__ long long red_ll[32];
   const int row = blockIdx.x;
+  qs_trace(QS_K_NORM, 0);
   pdl_wait();
+  qs_trace(QS_K_NORM, 1);
   if (threadIdx.x == 0) pdl_launch_dependents();
   load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
   __syncthreads();
@@ -131,14 +152,14 @@ __global__ void __launch_bounds__(kThreads) layernorm_quant_kernel(int8_t* __res
   amax = block_reduce(amax, red, OpMax(), 0.f);  // (includes the barrier that publishes sy)
   if (input_sum) {
     // reference thread t (of ref_block threads) accumulates y_h[t], y_h[t+B], ... sequentially IN FP16 (:275,286)
-    float part = 0.f;
+    long long part = 0;
     for (int t = threadIdx.x; t < ref_block; t += blockDim.x) {
       __half acc = __float2half_rn(0.f);
       for (int i = t; i < H; i += ref_block) acc = __hadd(acc, sy[i]);
-      part += __half2float(acc);
+      part += fx_of_half(__half2float(acc));
     }
-    const float total = block_reduce(part, red, OpSum(), 0.f);
-    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+    const long long total = block_sum_ll(part, red_ll);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(fx_to_float(total));
   }
   if (threadIdx.x == 0) scaling[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
   const float qs_ = __fdiv_rn(127.f, amax);
@@ -169,8 +190,11 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
   __half* sx = reinterpret_cast<__half*>(sm);
   __half* sy = sx + H;
   __shared__ float red[32];
+  __shared__ long long red_ll[32];
   const int row = blockIdx.x;
+  qs_trace(QS_K_ADDNORM, 0);
   pdl_wait();
+  qs_trace(QS_K_ADDNORM, 1);
   if (threadIdx.x == 0) pdl_launch_dependents();
   {
     const uint4* a = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
@@ -234,14 +258,14 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
   }
   amax = block_reduce(amax, red, OpMax(), 0.f);
   if (input_sum) {
-    float part = 0.f;
+    long long part = 0;
     for (int t = threadIdx.x; t < ref_block; t += blockDim.x) {
       __half acc = __float2half_rn(0.f);
       for (int i = t; i < H; i += ref_block) acc = __hadd(acc, sy[i]);
-      part += __half2float(acc);
+      part += fx_of_half(__half2float(acc));
     }
-    const float total = block_reduce(part, red, OpSum(), 0.f);
-    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+    const long long total = block_sum_ll(part, red_ll);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(fx_to_float(total));
   }
   if (threadIdx.x == 0) scaling[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
   const float qs_ = __fdiv_rn(127.f, amax);
@@ -262,18 +286,27 @@ __device__ __forceinline__ __half silu_h_fused(__half x) {
   return __float2half_rn(__fdiv_rn(f, __fadd_rn(1.0f, expf(-f))));
 }
 
+// One row is split across a cluster of `csize` CTAs (all SMs busy even at 64 tokens); the row amax / sum are exchanged
+// through distributed shared memory.  grid.x = tokens * csize.
 __global__ void __launch_bounds__(kFusedThreads) silu_mul_quant_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
-                                                                      __half* __restrict__ input_sum, __half* __restrict__ scale, int d) {
+                                                                      __half* __restrict__ input_sum, __half* __restrict__ scale, int d, int csize) {
   extern __shared__ __align__(16) uint8_t sm[];
-  __half* sa = reinterpret_cast<__half*>(sm);  // activation row (fp16), d elements
+  __half* sa = reinterpret_cast<__half*>(sm);  // this CTA's slice of the activation row (fp16)
   __shared__ float red[32];
-  const int row = blockIdx.x;
+  __shared__ long long red_ll[32];
+  __shared__ __align__(16) long long s_part[2];  // [0] = bits of the local amax (float), [1] = local fixed-point sum
+  const int row = blockIdx.x / csize;
+  const int rank = blockIdx.x - row * csize;
+  const int dl = d / csize;  // columns of this CTA (multiple of 8)
+  qs_trace(QS_K_SILUQ, 0);
   pdl_wait();
+  qs_trace(QS_K_SILUQ, 1);
   if (threadIdx.x == 0) pdl_launch_dependents();
-  const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d);
-  const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d);
-  float amax = 0.f, s = 0.f;
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
+  const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + static_cast<size_t>(rank) * dl);
+  const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d + static_cast<size_t>(rank) * dl);
+  float amax = 0.f;
+  long long s = 0;
+  for (int i = threadIdx.x; i < dl / 8; i += blockDim.x) {
     const uint4 x = __ldg(gx + i), y = __ldg(gy + i);
     const __half* xh = reinterpret_cast<const __half*>(&x);
     const __half* yh = reinterpret_cast<const __half*>(&y);
@@ -283,26 +316,48 @@ __global__ void __launch_bounds__(kFusedThreads) silu_mul_quant_kernel(int8_t* _
     for (int j = 0; j < 8; ++j) {
       oh[j] = __hmul(silu_h_fused(xh[j]), yh[j]);
       const float f = __half2float(oh[j]);
-      s += f;
+      if (input_sum) s += fx_of_half(f);
       amax = fmaxf(amax, fabsf(f));
     }
     reinterpret_cast<uint4*>(sa)[i] = o;
   }
   amax = block_reduce(amax, red, OpMax(), 0.f);  // (the barriers inside also publish sa)
-  if (input_sum) {
-    const float total = block_reduce(s, red, OpSum(), 0.f);
-    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+  long long total = 0;
+  if (input_sum) total = block_sum_ll(s, red_ll);
+  if (csize > 1) {
+    if (threadIdx.x == 0) {
+      s_part[0] = __float_as_int(amax);
+      s_part[1] = total;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(s_part));
+    amax = 0.f;
+    total = 0;
+    for (int r = 0; r < csize; ++r) {
+      uint32_t peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(base), "r"(r));
+      long long a, b;
+      asm volatile("ld.shared::cluster.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(peer) : "memory");
+      amax = fmaxf(amax, __int_as_float(static_cast<int>(a)));
+      total += b;
+    }
   }
-  if (threadIdx.x == 0) scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+  if (rank == 0 && threadIdx.x == 0) {
+    scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+    if (input_sum) input_sum[row] = __float2half_rn(fx_to_float(total));
+  }
   const float qs_ = __fdiv_rn(127.f, amax);
-  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) {
+  int8_t* orow = out + static_cast<size_t>(row) * d + static_cast<size_t>(rank) * dl;
+  for (int i = threadIdx.x; i < dl / 8; i += blockDim.x) {
     const uint4 v = reinterpret_cast<const uint4*>(sa)[i];
     const __half* h = reinterpret_cast<const __half*>(&v);
     float x[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = __half2float(h[j]);
-    store_q8(out + static_cast<size_t>(row) * d, i, x, qs_);
+    store_q8(orow, i, x, qs_);
   }
+  // peers may still be reading s_part
+  if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,26 +368,30 @@ __global__ void __launch_bounds__(kThreads) quant_per_token_kernel(int8_t* __res
   extern __shared__ __align__(16) uint8_t sm[];
   __half* sx = reinterpret_cast<__half*>(sm);
   __shared__ float red[32];
+  __shared__ long long red_ll[32];
   const int row = blockIdx.x;
+  qs_trace(QS_K_QUANT, 0);
   pdl_wait();
+  qs_trace(QS_K_QUANT, 1);
   if (threadIdx.x == 0) pdl_launch_dependents();
   load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
   __syncthreads();
-  float amax = 0.f, s = 0.f;
+  float amax = 0.f;
+  long long s = 0;
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
     const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
     const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
-      s += f.x + f.y;
+      if (input_sum) s += fx_of_half(f.x) + fx_of_half(f.y);
       amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
     }
   }
   amax = block_reduce(amax, red, OpMax(), 0.f);
   if (input_sum) {
-    const float total = block_reduce(s, red, OpSum(), 0.f);
-    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(total);
+    const long long total = block_sum_ll(s, red_ll);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(fx_to_float(total));
   }
   if (threadIdx.x == 0) scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
   const float qs_ = __fdiv_rn(127.f, amax);
@@ -362,7 +421,9 @@ __global__ void __launch_bounds__(kThreads) rms_norm_kernel(void* __restrict__ o
   __half* sx = reinterpret_cast<__half*>(sm);
   __shared__ float red[32];
   const int row = blockIdx.x;
+  qs_trace(QS_K_RMS, 0);
   pdl_wait();
+  qs_trace(QS_K_RMS, 1);
   if (threadIdx.x == 0) pdl_launch_dependents();
   load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
   __syncthreads();
@@ -408,7 +469,9 @@ __device__ __forceinline__ __half silu_h(__half x) {
 
 __global__ void __launch_bounds__(kThreads) silu_and_mul_kernel(__half* __restrict__ out, const __half* __restrict__ in, int d) {
   const int row = blockIdx.x;
+  qs_trace(QS_K_SILU, 0);
   pdl_wait();
+  qs_trace(QS_K_SILU, 1);
   if (threadIdx.x == 0) pdl_launch_dependents();
   const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d);
   const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d);
@@ -539,12 +602,14 @@ int launch(Kern kern, dim3 grid, dim3 block, size_t smem, void* stream, const ch
 
 template <typename Kern>
 int ensure_smem(Kern kern, size_t bytes, const char* what) {
-  if (bytes <= 48 * 1024) return QS_OK;
+  if (bytes <= 40 * 1024) return QS_OK;  // static shared memory of the kernel comes on top of the dynamic row
   QS_REQUIRE(bytes <= 200 * 1024, "%s: row of %zu bytes does not fit in shared memory", what, bytes);
   return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), what);
 }
 
 }  // namespace
+
+int elementwise_trace_install(void* buf, unsigned cap) { return qs_trace_install(buf, cap); }
 
 int rms_norm(void* out, const void* in, const void* weight, float eps, int use_quant, int tokens, int hidden, void* stream) {
   if (tokens == 0) return QS_OK;
@@ -636,11 +701,29 @@ int dequant_silu_and_mul_quant(void* out_q, const void* in_i32, float scale_gate
 int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int d, void* stream) {
   if (tokens == 0) return QS_OK;
   QS_REQUIRE(d > 0 && d % 8 == 0, "silu_and_mul_quant: d=%d must be a positive multiple of 8", d);
-  const size_t smem = static_cast<size_t>(d) * 2;
+  // split a row over a cluster so that tokens * csize CTAs fill the machine (each CTA keeps >= 512 columns)
+  int csize = 1;
+  while (csize < 8 && tokens * csize < 2 * 148 && d % (csize * 2 * 8) == 0 && d / (csize * 2) >= 512) csize *= 2;
+  const size_t smem = static_cast<size_t>(d / csize) * 2;
   int rc = ensure_smem(silu_mul_quant_kernel, smem, "silu_and_mul_quant");
   if (rc) return rc;
-  return launch(silu_mul_quant_kernel, dim3(tokens), dim3(kFusedThreads), smem, stream, "silu_and_mul_quant", static_cast<int8_t*>(out_q),
-                static_cast<const __half*>(in), static_cast<__half*>(input_sum), static_cast<__half*>(scale), d);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tokens * csize);
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = csize;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return check_cuda(cudaLaunchKernelEx(&cfg, silu_mul_quant_kernel, static_cast<int8_t*>(out_q), static_cast<const __half*>(in),
+                                       static_cast<__half*>(input_sum), static_cast<__half*>(scale), d, csize),
+                    "silu_and_mul_quant");
 }
 
 int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void* delta, const void* gamma, void* input_sum, void* scaling,

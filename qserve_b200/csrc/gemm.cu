@@ -156,6 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   const int kb_begin = (KB * rank) / S, kb_end = (KB * (rank + 1)) / S;
   const int n_kb = kb_end - kb_begin;
   if (threadIdx.x == 0) QS_PROF(0);
+  qs_trace(QS_K_GEMM, 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_act);
@@ -208,6 +209,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       for (int it = 0; it < pre; ++it) issue_w(it, it);
       pdl_wait();
       QS_PROF(2);
+      qs_trace(QS_K_GEMM, 1);
       for (int it = 0; it < pre; ++it) issue_a(it, it);
       int s = 0;
       uint32_t ph = 0;  // parity of the (it / STAGES - 1)-th completion of empty[s]
@@ -391,6 +393,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   // no CTA may exit (and free its shared memory) while peers are still reading it
   if (S > 1) cluster_sync_all(); else __syncthreads();
   if (threadIdx.x == 0) QS_PROF(12);
+  qs_trace(QS_K_GEMM, 2);
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
@@ -536,6 +539,7 @@ int dispatch_gemm(const GemmArgs& a) {
 int gemm_w4a8_per_chn(const GemmArgs& a) { return dispatch_gemm<kModeW4Chn>(a); }
 int gemm_w4a8_per_group(const GemmArgs& a) { return dispatch_gemm<kModeW4Grp>(a); }
 int gemm_w8a8(const GemmArgs& a) { return dispatch_gemm<kModeW8>(a); }
-size_t gemm_workspace_bytes() { return 4096; }  // the cluster/DSMEM split-K needs no global workspace; kept for ABI stability
+size_t gemm_workspace_bytes() { return 4096; }
+int gemm_trace_install(void* buf, unsigned cap) { return qs_trace_install(buf, cap); }  // the cluster/DSMEM split-K needs no global workspace; kept for ABI stability
 
 }  // namespace qs

@@ -30,6 +30,9 @@ int gemm_w4a8_per_chn(const GemmArgs& a);
 int gemm_w4a8_per_group(const GemmArgs& a);
 int gemm_w8a8(const GemmArgs& a);
 size_t gemm_workspace_bytes();
+int gemm_trace_install(void* buf, unsigned cap);
+int attention_trace_install(void* buf, unsigned cap);
+int elementwise_trace_install(void* buf, unsigned cap);
 
 // elementwise.cu
 int rms_norm(void* out, const void* in, const void* weight, float eps, int use_quant, int tokens, int hidden, void* stream);
@@ -59,6 +62,9 @@ struct DecodeAttnArgs {
   const long long* kv_pointers = nullptr;  // [B, 2, max_blocks] absolute device addresses
   const int* lengths = nullptr;            // [B] context length including the new token
   void* out = nullptr;                     // fp16 [B, Hq, D] contiguous
+  void* q_out = nullptr;                   // fused-quant extension: int8 [B, Hq*D] (then `out` is not written)
+  void* q_scale = nullptr;                 //   fp16 [B]
+  void* q_sum = nullptr;                   //   fp16 [B] or null
   int batch = 0, num_heads = 0, num_kv_heads = 0, head_dim = 0, max_blocks = 0;
   int tokens_per_block = 64, size_per_token = 0, timestep = 0, memory_max_len = 0;
   int rotary_dim = 0;

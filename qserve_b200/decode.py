@@ -205,6 +205,15 @@ class DecodeRunner:
             self.max_seq_len, D, cfg.rope_theta, True, self.kv_bits == 4, True)  # :265-281
         return attn.reshape(q.size(0), -1)
 
+    def _attention_quant(self, li, qsum) -> bool:
+        cfg, D = self.cfg, self.cfg.head_dim
+        q, k, v = self.qkv_buf.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
+        q = q.reshape(q.size(0), self.Hq, D)
+        k = k.reshape(k.size(0), self.Hkv, D)
+        v = v.reshape(v.size(0), self.Hkv, D)
+        return _ext.single_query_attention_quant(q, k, v, self.block_tables[li], self.context_lens, min(8192, cfg.max_pos), 64, self.size_per_token,
+                                                 self.max_seq_len, D, cfg.rope_theta, self.kv_bits == 4, True, self.q_attn, self.q_scale, qsum)
+
     def _forward_reference(self, tokens: torch.Tensor) -> torch.Tensor:
         """Exactly the reference's op sequence (LlamaDecoderLayer.forward, llama_w4a8_unpad.py:330-361)."""
         cfg = self.cfg
@@ -246,8 +255,10 @@ class DecodeRunner:
         n += 1
         for li, ly in enumerate(self.layers):
             ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
-            attn = self._attention(li)
-            self._quant(self.q_attn, attn)
+            if not self._attention_quant(li, qsum):
+                attn = self._attention(li)
+                self._quant(self.q_attn, attn)
+                n += 1
             ly["o"](self.q_attn, self.q_scale, self.q_sum, self.out_buf)
             self._allreduce(self.out_buf)
             _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, ly["ln2"], qsum, self.q_scale, cfg.eps)
@@ -256,7 +267,7 @@ class DecodeRunner:
             _ext.silu_and_mul_quant(self.q_mlp, self.gate_up_buf, qsum, self.q_scale)
             ly["down"](self.q_mlp, self.q_scale, self.q_sum, self.out_buf)
             self._allreduce(self.out_buf)
-            n += 8
+            n += 7
             if li + 1 < len(self.layers):
                 _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, self.layers[li + 1]["ln1"], qsum, self.q_scale, cfg.eps)
                 hidden, nxt = nxt, hidden
