@@ -153,13 +153,14 @@ QS_API int qs_dequant_silu_and_mul_quant(int8_t* out, const int32_t* input, floa
 QS_API int qs_add_rms_norm_general(int8_t* out, void* hidden_out, const void* x, const void* delta, const void* weight, void* input_sum,
                                    void* scaling, float epsilon, int tokens, int hidden, void* stream);
 /* single_query_attention followed by invoke_quant[_fuse_sum] of the [B, Hq*D] result: out_q int8 [B, Hq*D], out_scale fp16 [B],
- * out_sum fp16 [B] or NULL.  The CTAs of one token form a thread-block cluster and exchange the row amax / sum through
- * distributed shared memory.  Returns QS_ERR_UNSUPPORTED when a token needs more than 8 CTAs (callers then run the two ops). */
+ * out_sum fp16 [B] or NULL.  The fp16 attention row stays in `workspace` (>= qs_attention_workspace_bytes, zero-initialised
+ * once, L2 resident); the last CTA of a token to finish quantises it, so the result is bit-identical to the two-op sequence. */
 QS_API int qs_single_query_attention_quant(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride, int64_t v_stride,
                                            const int64_t* kv_pointers, const int32_t* length_per_sample, int8_t* out_q, void* out_scale,
                                            void* out_sum, int batch, int num_heads, int num_kv_heads, int head_dim, int max_blocks_per_seq,
                                            int memory_max_seqlen, int tokens_per_block, int size_per_token, int timestep,
-                                           int rotary_embedding_dim, float rotary_base, int int4_kv_cache, int kv_cache_with_zeros, void* stream);
+                                           int rotary_embedding_dim, float rotary_base, int int4_kv_cache, int kv_cache_with_zeros, void* workspace,
+                                           size_t workspace_bytes, void* stream);
 /* silu_and_mul(input [tokens, 2d]) followed by invoke_quant[_fuse_sum](out, act, input_sum | NULL, scale)                 */
 QS_API int qs_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int tokens, int d, void* stream);
 

@@ -385,20 +385,20 @@ def silu_and_mul_quant(out, input, input_sum: Optional[torch.Tensor], scale) -> 
 
 def single_query_attention_quant(q, k, v, kv_pointers, length_per_sample, memory_max_seqlen: int, tokens_per_block: int, size_per_token: int,
                                  timestep: int, rotary_embedding_dim: int, rotary_base: float, int4_kv_cache: bool, kv_cache_with_zeros: bool,
-                                 out_q, out_scale, out_sum: Optional[torch.Tensor]) -> bool:
-    """single_query_attention + invoke_quant[_fuse_sum] in one launch (cluster/DSMEM row reduction).
-    Returns False (nothing launched) when the shape is not supported; the caller then runs the two reference ops."""
+                                 out_q, out_scale, out_sum: Optional[torch.Tensor]) -> None:
+    """single_query_attention + invoke_quant[_fuse_sum] in one launch: out_q int8 [B, Hq*D], out_scale / out_sum fp16 [B].
+    Bit-identical to the two reference ops run back to back (llama_w4a8_unpad.py:265-283)."""
     batch = kv_pointers.size(0)
+    if batch == 0:
+        return
     nheads, nheads_kv, headdim = q.size(1), k.size(1), k.size(-1)
-    g = nheads // nheads_kv
-    if nheads_kv * ((g + 7) // 8) > 8:
-        return False
     _require(q.dtype == _HALF and q.stride(2) == 1 and q.stride(1) == headdim, "q must be float16 with stride(1) == head_dim")
     _require(k.stride(1) == headdim and v.stride(1) == headdim and kv_pointers.is_contiguous(), "k, v, kv_pointers layout")
+    _require(out_q.dtype == torch.int8 and out_q.is_contiguous() and out_q.numel() == batch * nheads * headdim, "out_q must be int8 [B, Hq*D]")
+    ws = attention_workspace(q.device, batch, nheads, headdim)
     check(lib.qs_single_query_attention_quant(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0), kv_pointers.data_ptr(),
                                               length_per_sample.data_ptr(), out_q.data_ptr(), out_scale.data_ptr(),
                                               out_sum.data_ptr() if out_sum is not None else None, batch, nheads, nheads_kv, headdim,
                                               kv_pointers.size(-1), int(memory_max_seqlen), int(tokens_per_block), int(size_per_token), int(timestep),
                                               int(rotary_embedding_dim), float(rotary_base), int(bool(int4_kv_cache)), int(bool(kv_cache_with_zeros)),
-                                              _stream(q)))
-    return True
+                                              ws.data_ptr(), ws.numel(), _stream(q)))

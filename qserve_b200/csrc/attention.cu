@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kAttnThreadsV2, 4)
 decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restrict__ k_in, const __half* __restrict__ v_in, long long q_stride,
                         long long k_stride, long long v_stride, const long long* __restrict__ kv_pointers, const int* __restrict__ lengths,
                         __half* __restrict__ out, int num_heads, int num_kv_heads, int max_blocks, PageGeom pg, float rotary_base, int rotary_dim,
-                        int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt, int8_t* __restrict__ q_out,
+                        int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt, uint32_t* __restrict__ tok_cnt, int8_t* __restrict__ q_out,
                         __half* __restrict__ q_scale, __half* __restrict__ q_sum) {
   using SL = StageLayout<BITS>;
   constexpr int R = SL::kStages;
@@ -496,9 +496,6 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 
   // ---------------- merge the warps (and the un-quantised new token); one output dim per thread ----------------
   const bool owner = (split == 0);
-  __half hq[kMaxG];      // fused-quant mode: this thread's outputs, kept for the second pass
-  float amax_l = 0.f;
-  long long sum_l = 0;
   if (threadIdx.x < kD) {
     const int d = threadIdx.x;
     const int nparts = kWarps + (owner ? 1 : 0);
@@ -522,15 +519,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
         }
         if (nsplit == 1) {
           // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
-          const __half h = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
-          if (q_out == nullptr) {
-            out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = h;
-          } else {
-            hq[r] = h;
-            const float f = __half2float(h);
-            amax_l = fmaxf(amax_l, fabsf(f));
-            sum_l += __float2ll_rn(f * 16777216.f);
-          }
+          out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
         } else {
           float* pr = part + static_cast<size_t>(r) * nsplit * (kD + 2);
           pr[d] = acc;
@@ -542,56 +531,8 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       }
     }
   }
-  if (q_out != nullptr) {
-    // ---- fused per-token INT8 quantisation of the attention output (invoke_quant[_fuse_sum], fused_kernels.cu:92-137):
-    //      the token row spans all CTAs of the cluster (one per kv head); amax / exact sum exchanged through DSMEM ----
-    __shared__ float s_red_f[8];
-    __shared__ long long s_red_l[8];
-    __shared__ __align__(16) long long s_part[2];
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      amax_l = fmaxf(amax_l, __shfl_xor_sync(0xffffffffu, amax_l, m));
-      sum_l += __shfl_xor_sync(0xffffffffu, sum_l, m);
-    }
-    if (lane == 0) { s_red_f[warp] = amax_l; s_red_l[warp] = sum_l; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float a = 0.f;
-      long long t = 0;
-      for (int w = 0; w < kAttnThreadsV2 / 32; ++w) { a = fmaxf(a, s_red_f[w]); t += s_red_l[w]; }
-      s_part[0] = __float_as_int(a);
-      s_part[1] = t;
-    }
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(s_part));
-    float amax = 0.f;
-    long long total = 0;
-    for (int r = 0; r < static_cast<int>(gridDim.x); ++r) {
-      uint32_t peer;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(base), "r"(r));
-      long long a, t;
-      asm volatile("ld.shared::cluster.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(t) : "r"(peer) : "memory");
-      amax = fmaxf(amax, __int_as_float(static_cast<int>(a)));
-      total += t;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      q_scale[b] = __float2half_rn(__fdiv_rn(amax, 127.f));
-      if (q_sum) q_sum[b] = __float2half_rn(__ll2float_rn(total) * (1.f / 16777216.f));
-    }
-    if (threadIdx.x < kD) {
-      const float qs_ = __fdiv_rn(127.f, amax);
-#pragma unroll
-      for (int r = 0; r < kMaxG; ++r) {
-        if (r < Gc) {
-          int32_t c;
-          asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(c) : "f"(__fmul_rn(__half2float(hq[r]), qs_)));
-          q_out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + threadIdx.x] = static_cast<int8_t>(c);
-        }
-      }
-    }
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-  }
   qs_trace(QS_K_ATTN, 2);
+  bool final_written = (nsplit == 1);  // this CTA produced the final fp16 outputs of its head group
   if (nsplit > 1) {
     __threadfence();
     __syncthreads();
@@ -603,6 +544,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       s_last = last ? 1u : 0u;
     }
     __syncthreads();
+    final_written = (s_last != 0);
     if (s_last && threadIdx.x < kD) {
       const int d = threadIdx.x;
       __threadfence();
@@ -618,6 +560,68 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
           acc += __ldcg(pr + sp * (kD + 2) + d) * e;
         }
         out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
+      }
+    }
+  }
+  if (q_out != nullptr && final_written) {
+    // ---- fused per-token INT8 quantisation of the attention output (invoke_quant[_fuse_sum], fused_kernels.cu:92-137).
+    //      `out` is an fp16 scratch row in the workspace (L2 resident); the last head-group CTA of a token to finish
+    //      re-reads the row and quantises it: same arithmetic as quant_per_token_kernel ----
+    __shared__ uint32_t s_last_tok;
+    __shared__ float s_red_f[8];
+    __shared__ long long s_red_l[8];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t old = atomicAdd(tok_cnt + b, 1u);
+      const bool last = (old == gridDim.x - 1);
+      if (last) tok_cnt[b] = 0;
+      s_last_tok = last ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last_tok) {
+      __threadfence();
+      const int nvec = num_heads * kD / 8;
+      const uint4* row = reinterpret_cast<const uint4*>(out + static_cast<size_t>(b) * num_heads * kD);
+      float amax = 0.f;
+      long long sum = 0;
+      for (int i = threadIdx.x; i < nvec; i += kAttnThreadsV2) {
+        const uint4 v = __ldcg(row + i);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          if (q_sum) sum += __float2ll_rn(f.x * 16777216.f) + __float2ll_rn(f.y * 16777216.f);
+          amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+        }
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, m));
+        sum += __shfl_xor_sync(0xffffffffu, sum, m);
+      }
+      if (lane == 0) { s_red_f[warp] = amax; s_red_l[warp] = sum; }
+      __syncthreads();
+      amax = 0.f;
+      sum = 0;
+      for (int w = 0; w < kAttnThreadsV2 / 32; ++w) { amax = fmaxf(amax, s_red_f[w]); sum += s_red_l[w]; }
+      if (threadIdx.x == 0) {
+        q_scale[b] = __float2half_rn(__fdiv_rn(amax, 127.f));
+        if (q_sum) q_sum[b] = __float2half_rn(__ll2float_rn(sum) * (1.f / 16777216.f));
+      }
+      const float qs_ = __fdiv_rn(127.f, amax);
+      uint2* qrow = reinterpret_cast<uint2*>(q_out + static_cast<size_t>(b) * num_heads * kD);
+      for (int i = threadIdx.x; i < nvec; i += kAttnThreadsV2) {
+        const uint4 v = __ldcg(row + i);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+        uint32_t w[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int32_t c;
+          asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(c) : "f"(__fmul_rn(__half2float(h[j]), qs_)));
+          w[j >> 2] |= (static_cast<uint32_t>(c) & 0xffu) << ((j & 3) * 8);
+        }
+        qrow[i] = make_uint2(w[0], w[1]);
       }
     }
   }
@@ -744,12 +748,14 @@ int launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, void* stream, cons
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, args...), what);
 }
 
-constexpr size_t kAttnCounterBytes = 256 * 1024;  // 65536 (sequence, head-group) counters
+constexpr size_t kAttnCounterBytes = 256 * 1024;  // 49152 (sequence, head-group) split counters + 16384 per-token counters
+constexpr size_t kAttnTokCounterOffset = 192 * 1024;
 
 }  // namespace
 
 size_t attention_workspace_bytes(int batch, int num_heads, int head_dim, int max_splits) {
-  return kAttnCounterBytes + static_cast<size_t>(batch) * num_heads * max_splits * (head_dim + 2) * sizeof(float);
+  return kAttnCounterBytes + static_cast<size_t>(batch) * num_heads * max_splits * (head_dim + 2) * sizeof(float) +
+         static_cast<size_t>(batch) * num_heads * head_dim * sizeof(__half);  // + fp16 scratch rows of the fused-quant form
 }
 
 int attention_trace_install(void* buf, unsigned cap) { return qs_trace_install(buf, cap); }
@@ -784,7 +790,7 @@ int decode_attention(const DecodeAttnArgs& a) {
   uint32_t* cnt = nullptr;
   if (nsplit > 1) {
     const size_t need = attention_workspace_bytes(a.batch, a.num_heads, kD, nsplit);
-    if (a.workspace == nullptr || need > a.workspace_bytes || static_cast<size_t>(a.batch) * gx * 4 > kAttnCounterBytes) {
+    if (a.workspace == nullptr || need > a.workspace_bytes || static_cast<size_t>(a.batch) * gx * 4 > kAttnTokCounterOffset) {
       nsplit = 1;
     } else {
       cnt = static_cast<uint32_t*>(a.workspace);
@@ -792,10 +798,16 @@ int decode_attention(const DecodeAttnArgs& a) {
     }
   }
   const bool fused_quant = a.q_out != nullptr;
+  uint32_t* tok_cnt = nullptr;
+  void* out = a.out;
   if (fused_quant) {
-    if (gx > 8) return set_error(QS_ERR_UNSUPPORTED, "single_query_attention_quant: %d CTAs per token exceed the portable cluster size (8)", gx);
     QS_REQUIRE(a.q_scale != nullptr, "single_query_attention_quant: q_scale is null");
-    nsplit = 1;
+    const size_t row_bytes = static_cast<size_t>(a.batch) * a.num_heads * kD * sizeof(__half);
+    const size_t part_bytes = nsplit > 1 ? attention_workspace_bytes(a.batch, a.num_heads, kD, nsplit) - kAttnCounterBytes - row_bytes : 0;
+    QS_REQUIRE(a.workspace != nullptr && a.workspace_bytes >= kAttnCounterBytes + part_bytes + row_bytes && a.batch <= 16384,
+               "single_query_attention_quant: workspace too small (need qs_attention_workspace_bytes)");
+    tok_cnt = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(a.workspace) + kAttnTokCounterOffset);
+    out = static_cast<uint8_t*>(a.workspace) + kAttnCounterBytes + part_bytes;
   }
   dim3 grid(gx, a.batch, nsplit);
   auto run = [&](auto kern, size_t smem) {
@@ -815,15 +827,15 @@ int decode_attention(const DecodeAttnArgs& a) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = fused_quant ? gx : 1;
+    attr[1].val.clusterDim.x = 1;
     attr[1].val.clusterDim.y = 1;
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(a.q),
                       static_cast<const __half*>(a.k), static_cast<const __half*>(a.v), a.q_stride, a.k_stride, a.v_stride, a.kv_pointers, a.lengths,
-                      static_cast<__half*>(a.out), a.num_heads, a.num_kv_heads, a.max_blocks, pg, a.rotary_base, a.rotary_dim, a.timestep, nsplit,
-                      part, cnt, static_cast<int8_t*>(a.q_out), static_cast<__half*>(a.q_scale), static_cast<__half*>(a.q_sum)), "single_query_attention");
+                      static_cast<__half*>(out), a.num_heads, a.num_kv_heads, a.max_blocks, pg, a.rotary_base, a.rotary_dim, a.timestep, nsplit,
+                      part, cnt, tok_cnt, static_cast<int8_t*>(a.q_out), static_cast<__half*>(a.q_scale), static_cast<__half*>(a.q_sum)), "single_query_attention");
   };
   QS_REQUIRE((a.timestep + 63) / 64 + 1 <= kMaxBlocksSmem, "single_query_attention: context of %d tokens exceeds the %d pages staged in shared memory", a.timestep, kMaxBlocksSmem);
   QS_REQUIRE(a.tokens_per_block == kPageTokens, "single_query_attention: tokens_per_block=%d, only 64 is supported (cache_engine block_size)", a.tokens_per_block);

@@ -205,13 +205,13 @@ class DecodeRunner:
             self.max_seq_len, D, cfg.rope_theta, True, self.kv_bits == 4, True)  # :265-281
         return attn.reshape(q.size(0), -1)
 
-    def _attention_quant(self, li, qsum) -> bool:
+    def _attention_quant(self, li, qsum) -> None:
         cfg, D = self.cfg, self.cfg.head_dim
         q, k, v = self.qkv_buf.split([self.q_size, self.kv_size, self.kv_size], dim=-1)
         q = q.reshape(q.size(0), self.Hq, D)
         k = k.reshape(k.size(0), self.Hkv, D)
         v = v.reshape(v.size(0), self.Hkv, D)
-        return _ext.single_query_attention_quant(q, k, v, self.block_tables[li], self.context_lens, min(8192, cfg.max_pos), 64, self.size_per_token,
+        _ext.single_query_attention_quant(q, k, v, self.block_tables[li], self.context_lens, min(8192, cfg.max_pos), 64, self.size_per_token,
                                                  self.max_seq_len, D, cfg.rope_theta, self.kv_bits == 4, True, self.q_attn, self.q_scale, qsum)
 
     def _forward_reference(self, tokens: torch.Tensor) -> torch.Tensor:
@@ -255,10 +255,7 @@ class DecodeRunner:
         n += 1
         for li, ly in enumerate(self.layers):
             ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
-            if not self._attention_quant(li, qsum):
-                attn = self._attention(li)
-                self._quant(self.q_attn, attn)
-                n += 1
+            self._attention_quant(li, qsum)
             ly["o"](self.q_attn, self.q_scale, self.q_sum, self.out_buf)
             self._allreduce(self.out_buf)
             _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, ly["ln2"], qsum, self.q_scale, cfg.eps)

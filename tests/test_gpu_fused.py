@@ -67,7 +67,8 @@ def test_fused_runner_matches_reference_sequence(dev, precision):
     (4, 32, 8, [17, 16, 64, 129], True),      # Llama-3 head geometry, no context split -> bit identical to the two-op sequence
     (3, 8, 2, [1, 65, 200], False),
     (2, 16, 1, [90, 257], True),              # two head groups per kv head
-    (2, 32, 8, [1025, 700], True),            # the unfused op splits the context here: same codes within 1 LSB
+    (2, 32, 8, [1025, 700], True),            # context splits: two-level last-CTA merge
+    (1, 64, 64, [2048], True),                # 64 CTAs per token
 ])
 def test_attention_quant_equals_attention_then_quant(dev, bits, B, Hq, Hkv, lens, with_sum):
     """single_query_attention_quant == invoke_quant[_fuse_sum](single_query_attention(...)); KV pages updated identically."""
@@ -93,8 +94,7 @@ def test_attention_quant_equals_attention_then_quant(dev, bits, B, Hq, Hkv, lens
         sm = torch.zeros(B, dtype=torch.half, device=dev)
         args = (8192, 64, Hkv * D * bits // 8, int(max(lens)), D, ROPE)
         if fused:
-            ok = ext.single_query_attention_quant(qd, kd, vd, table, lens_d, *args, bits == 4, True, oq, sc, sm if with_sum else None)
-            assert ok
+            ext.single_query_attention_quant(qd, kd, vd, table, lens_d, *args, bits == 4, True, oq, sc, sm if with_sum else None)
         else:
             out = fa.single_query_attention(qd, kd, vd, table, lens_d, None, *args, True, bits == 4, True).reshape(B, -1)
             if with_sum:
@@ -105,18 +105,4 @@ def test_attention_quant_equals_attention_then_quant(dev, bits, B, Hq, Hkv, lens
         res.append((oq.cpu(), sc.cpu(), sm.cpu(), gk.download(), gv.download()))
     (q1, s1, m1, k1, v1), (q2, s2, m2, k2, v2) = res
     assert np.array_equal(k1, k2) and np.array_equal(v1, v2)
-    if max(lens) <= 512:
-        assert torch.equal(q1, q2) and torch.equal(s1, s2) and torch.equal(m1, m2)
-    else:
-        assert (q1.int() - q2.int()).abs().max() <= 1
-        assert (s1.float() - s2.float()).abs().max() <= 2e-3 * s1.float().abs().max()
-        assert (m1.float() - m2.float()).abs().max() <= 0.05
-
-
-def test_attention_quant_unsupported_shape_falls_back(dev):
-    from qserve_b200 import backend as ext
-    q = torch.zeros((1, 64, 128), dtype=torch.half, device=dev)
-    k = torch.zeros((1, 64, 128), dtype=torch.half, device=dev)
-    table = torch.zeros((1, 2, 1), dtype=torch.int64, device=dev)
-    lens = torch.ones(1, dtype=torch.int32, device=dev)
-    assert ext.single_query_attention_quant(q, k, k, table, lens, 8192, 64, 64 * 64, 1, 128, 1e4, True, True, None, None, None) is False
+    assert torch.equal(q1, q2) and torch.equal(s1, s2) and torch.equal(m1, m2)
