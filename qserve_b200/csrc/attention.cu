@@ -59,6 +59,11 @@ __device__ __forceinline__ uint32_t pack_f2h2(float lo, float hi) {
   return d;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr uint32_t kMagic = 0x64006400u;      // half2(1024, 1024)
 constexpr uint32_t kSixteenth = 0x2c002c00u;  // half2(1/16)
 constexpr uint32_t kNeg64 = 0xd400d400u;      // half2(-64)
@@ -175,14 +180,14 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], kWarps);
+      mbar_init(&s_empty[i], 2);  // the two consumer warps that share a page
     }
     fence_barrier_init();
   }
   qs_trace(QS_K_ATTN, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_ATTN, 1);
-  if (threadIdx.x == 0) pdl_launch_dependents();
 
   const int tlen = (lengths ? lengths[b] : timestep) - 1;  // tokens already in the cache (Template.hpp:901)
   const long long* kptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 0) * max_blocks;
@@ -285,21 +290,35 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
     // ---- Q as the MMA "B" operand (n = head g), permuted to the in-register order of the unpacked codes; sum(q) per head ----
     uint32_t qb0[8], qb1[8];
     float sumq0, sumq1;  // heads 2*q4 and 2*q4+1 (this thread's S^T columns)
+    // The tensor-core operands are the codes with the fp16 magic exponent still attached: 1024 + u (low nibble / byte) or
+    // 1024 + 16 u (high nibble, the matching Q entries are pre-scaled by 1/16).  The constant part is removed after the MMA:
+    //   sum_d (1024 + w_d u_d) q'_d = B(q) + sum_d u_d q_d ,   B(q) = 1024 sum_{low} q_d + 64 sum_{high} q_d
+    float biasq0, biasq1;
     {
       const __half* qr = s_q + g * kD + 32 * q4;
-      float acc = 0.f;
+      float acc_e = 0.f, acc_o = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc += __half2float(qr[j]);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      for (int j = 0; j < 32; j += 2) {
+        acc_e += __half2float(qr[j]);
+        acc_o += __half2float(qr[j + 1]);
+      }
+      acc_e += __shfl_xor_sync(0xffffffffu, acc_e, 1);
+      acc_o += __shfl_xor_sync(0xffffffffu, acc_o, 1);
+      acc_e += __shfl_xor_sync(0xffffffffu, acc_e, 2);
+      acc_o += __shfl_xor_sync(0xffffffffu, acc_o, 2);
+      const float acc = acc_e + acc_o;
+      const float bias = (BITS == 4) ? fmaf(1024.f, acc_e, 64.f * acc_o) : 1024.f * acc;  // KV4: odd dims sit in the high nibbles
       sumq0 = __shfl_sync(0xffffffffu, acc, (2 * q4) * 4);
       sumq1 = __shfl_sync(0xffffffffu, acc, (2 * q4 + 1) * 4);
+      biasq0 = __shfl_sync(0xffffffffu, bias, (2 * q4) * 4);
+      biasq1 = __shfl_sync(0xffffffffu, bias, (2 * q4 + 1) * 4);
+      const __half sixteenth = __float2half_rn(0.0625f);
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         if constexpr (BITS == 4) {
           const int d0 = 8 * (s >> 1) + 2 * (s & 1);  // k-step 2w: nibbles (0,4 | 1,5); 2w+1: (2,6 | 3,7) of word w
           qb0[s] = pack_h2(qr[d0], qr[d0 + 4]);
-          qb1[s] = pack_h2(qr[d0 + 1], qr[d0 + 5]);
+          qb1[s] = pack_h2(__hmul(qr[d0 + 1], sixteenth), __hmul(qr[d0 + 5], sixteenth));  // exact: a power of two
         } else {
           qb0[s] = pack_h2(qr[4 * s], qr[4 * s + 1]);
           qb1[s] = pack_h2(qr[4 * s + 2], qr[4 * s + 3]);
@@ -312,35 +331,46 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
     float o[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f, cr0 = 0.f, cr1 = 0.f;
+    // running max, sum p, sum p*c (zero-point correction), sum p' (bias correction of the V operand) per head
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f, cr0 = 0.f, cr1 = 0.f, sp0 = 0.f, sp1 = 0.f;
 
     // S^T = K Q^T: A rows g / g+8 <-> chunk tokens tokA / 8+tokA (the permutation keeps the V row reads at a 2-way conflict)
     const int tokA = (g & 1) * 4 + (g >> 1);
     constexpr int kRow = kD * BITS / 8;  // bytes per token row
-
-    int s = 0;
+    // warp w consumes tokens [32 (w & 1), +32) of the pages whose index has parity (w >> 1): two 16-token MMA chunks per
+    // iteration share one barrier wait, one max reduction and one set of address computations
+    const int hbase = (warp & 1) * 2 * kChunk;
+    int s = warp >> 1;
     uint32_t ph = 0;
-    for (int pidx = p_begin; pidx < p_end; ++pidx) {
+    for (int pidx = p_begin + (warp >> 1); pidx < p_end; pidx += 2) {
       mbar_wait(&s_full[s], ph);
       const uint8_t* st = s_ring + s * SL::kBytes;
-      const int t0 = pidx * kPageTokens + warp * kChunk;  // first token of this warp's chunk
+      const int t0 = pidx * kPageTokens + hbase;  // first token of this warp's 32-token slice
       if (t0 < tlen) {
-        // per-token (scale, aux) pairs: lanes 0..15 -> K tokens, lanes 16..31 -> V tokens of the chunk
+        // per-token (scale, aux) pairs of the 32 K and 32 V tokens
         {
-          const int tl = lane & 15;
-          const __half* sp = reinterpret_cast<const __half*>(st + (lane < 16 ? SL::kOffKs : SL::kOffVs)) + warp * kChunk + tl;
-          const __half sc = sp[0], zp = sp[64];
-          uint32_t packed;
-          if constexpr (BITS == 4) packed = pack_h2(sc, __float2half_rn(__fmul_rn(-__half2float(sc), __half2float(zp))));
-          else packed = pack_h2(sc, zp);
-          if (t0 + tl >= tlen) packed = 0u;  // unwritten slots: force finite zeros (their logits are masked below)
-          s_meta[s][lane >> 4][warp * kChunk + tl] = packed;
+          const __half* kp = reinterpret_cast<const __half*>(st + SL::kOffKs) + hbase + lane;
+          const __half* vp = reinterpret_cast<const __half*>(st + SL::kOffVs) + hbase + lane;
+          const __half ksc = kp[0], kzp = kp[64], vsc = vp[0], vzp = vp[64];
+          uint32_t pk, pv;
+          if constexpr (BITS == 4) {
+            pk = pack_h2(ksc, __float2half_rn(__fmul_rn(-__half2float(ksc), __half2float(kzp))));
+            pv = pack_h2(vsc, __float2half_rn(__fmul_rn(-__half2float(vsc), __half2float(vzp))));
+          } else {
+            pk = pack_h2(ksc, kzp);
+            pv = pack_h2(vsc, vzp);
+          }
+          if (t0 + lane >= tlen) pk = pv = 0u;  // unwritten slots: force finite zeros (their logits are masked below)
+          s_meta[s][0][hbase + lane] = pk;
+          s_meta[s][1][hbase + lane] = pv;
         }
         __syncwarp();
-        // ---- S^T (16 tokens x 8 heads) on raw codes: 8 MMAs ----
-        float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
-        {
-          const uint8_t* krow = st + SL::kOffK + (warp * kChunk + tokA) * kRow;
+        // ---- S^T (2 x 16 tokens x 8 heads) on biased codes: 16 MMAs ----
+        float sc[2][4];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          sc[c][0] = sc[c][1] = sc[c][2] = sc[c][3] = 0.f;
+          const uint8_t* krow = st + SL::kOffK + (hbase + c * kChunk + tokA) * kRow;
           if constexpr (BITS == 4) {
             const uint4 ka = *reinterpret_cast<const uint4*>(krow + q4 * 16);
             const uint4 kb = *reinterpret_cast<const uint4*>(krow + 8 * kRow + q4 * 16);
@@ -348,12 +378,10 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
               const uint32_t xa = wa[w], xb = wb[w], ta = xa >> 8, tb = xb >> 8;
-              mma_full(sc0, sc1, sc2, sc3, h2_sub(lop3_and_or(xa, 0x000f000fu, kMagic), kMagic), h2_sub(lop3_and_or(xb, 0x000f000fu, kMagic), kMagic),
-                       h2_fma(lop3_and_or(xa, 0x00f000f0u, kMagic), kSixteenth, kNeg64), h2_fma(lop3_and_or(xb, 0x00f000f0u, kMagic), kSixteenth, kNeg64),
-                       qb0[2 * w], qb1[2 * w]);
-              mma_full(sc0, sc1, sc2, sc3, h2_sub(lop3_and_or(ta, 0x000f000fu, kMagic), kMagic), h2_sub(lop3_and_or(tb, 0x000f000fu, kMagic), kMagic),
-                       h2_fma(lop3_and_or(ta, 0x00f000f0u, kMagic), kSixteenth, kNeg64), h2_fma(lop3_and_or(tb, 0x00f000f0u, kMagic), kSixteenth, kNeg64),
-                       qb0[2 * w + 1], qb1[2 * w + 1]);
+              mma_full(sc[c][0], sc[c][1], sc[c][2], sc[c][3], lop3_and_or(xa, 0x000f000fu, kMagic), lop3_and_or(xb, 0x000f000fu, kMagic),
+                       lop3_and_or(xa, 0x00f000f0u, kMagic), lop3_and_or(xb, 0x00f000f0u, kMagic), qb0[2 * w], qb1[2 * w]);
+              mma_full(sc[c][0], sc[c][1], sc[c][2], sc[c][3], lop3_and_or(ta, 0x000f000fu, kMagic), lop3_and_or(tb, 0x000f000fu, kMagic),
+                       lop3_and_or(ta, 0x00f000f0u, kMagic), lop3_and_or(tb, 0x00f000f0u, kMagic), qb0[2 * w + 1], qb1[2 * w + 1]);
             }
           } else {
             const uint4 ka0 = *reinterpret_cast<const uint4*>(krow + q4 * 32), ka1 = *reinterpret_cast<const uint4*>(krow + q4 * 32 + 16);
@@ -362,28 +390,42 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
             const uint32_t wb[8] = {kb0.x, kb0.y, kb0.z, kb0.w, kb1.x, kb1.y, kb1.z, kb1.w};
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-              // bytes -> fp16 integers: 0x6400 | u = 1024 + u, minus 1024 (exact)
-              mma_full(sc0, sc1, sc2, sc3, h2_sub(__byte_perm(wa[w], kMagic, 0x7150), kMagic), h2_sub(__byte_perm(wb[w], kMagic, 0x7150), kMagic),
-                       h2_sub(__byte_perm(wa[w], kMagic, 0x7352), kMagic), h2_sub(__byte_perm(wb[w], kMagic, 0x7352), kMagic), qb0[w], qb1[w]);
+              // bytes -> fp16: 0x6400 | u = 1024 + u
+              mma_full(sc[c][0], sc[c][1], sc[c][2], sc[c][3], __byte_perm(wa[w], kMagic, 0x7150), __byte_perm(wb[w], kMagic, 0x7150),
+                       __byte_perm(wa[w], kMagic, 0x7352), __byte_perm(wb[w], kMagic, 0x7352), qb0[w], qb1[w]);
             }
           }
         }
-        // ---- logits (log2 units) of tokens A = tokA, B = 8 + tokA for heads 2q4, 2q4+1; online softmax with lazy rescale ----
-        const uint32_t mkA = s_meta[s][0][warp * kChunk + tokA], mkB = s_meta[s][0][warp * kChunk + 8 + tokA];
-        const uint32_t mvA = s_meta[s][1][warp * kChunk + tokA], mvB = s_meta[s][1][warp * kChunk + 8 + tokA];
-        const float ksA = __half2float(__ushort_as_half(static_cast<uint16_t>(mkA & 0xFFFF))), ksB = __half2float(__ushort_as_half(static_cast<uint16_t>(mkB & 0xFFFF)));
-        const float vsA = __half2float(__ushort_as_half(static_cast<uint16_t>(mvA & 0xFFFF))), vsB = __half2float(__ushort_as_half(static_cast<uint16_t>(mvB & 0xFFFF)));
-        float kcA = __half2float(__ushort_as_half(static_cast<uint16_t>(mkA >> 16))), kcB = __half2float(__ushort_as_half(static_cast<uint16_t>(mkB >> 16)));
-        float vcA = __half2float(__ushort_as_half(static_cast<uint16_t>(mvA >> 16))), vcB = __half2float(__ushort_as_half(static_cast<uint16_t>(mvB >> 16)));
-        if constexpr (BITS == 8) {  // aux holds the zero point: c = -s * z
-          kcA = -ksA * kcA; kcB = -ksB * kcB; vcA = -vsA * vcA; vcB = -vsB * vcB;
+        // ---- logits (log2 units) of tokens A = tokA, B = 8 + tokA of both chunks for heads 2q4, 2q4+1 ----
+        float tl[2][4], vs[2][2], vc[2][2];
+        const bool partial = (t0 + 2 * kChunk > tlen);  // only the last page of a sequence
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t mkA = s_meta[s][0][hbase + c * kChunk + tokA], mkB = s_meta[s][0][hbase + c * kChunk + 8 + tokA];
+          const uint32_t mvA = s_meta[s][1][hbase + c * kChunk + tokA], mvB = s_meta[s][1][hbase + c * kChunk + 8 + tokA];
+          const float2 fkA = __half22float2(*reinterpret_cast<const __half2*>(&mkA)), fkB = __half22float2(*reinterpret_cast<const __half2*>(&mkB));
+          const float2 fvA = __half22float2(*reinterpret_cast<const __half2*>(&mvA)), fvB = __half22float2(*reinterpret_cast<const __half2*>(&mvB));
+          float ksA = fkA.x * sm_scale, ksB = fkB.x * sm_scale, kcA = fkA.y, kcB = fkB.y;
+          vs[c][0] = fvA.x; vs[c][1] = fvB.x; vc[c][0] = fvA.y; vc[c][1] = fvB.y;
+          if constexpr (BITS == 8) {  // aux holds the zero point: c = -s * z
+            kcA = -fkA.x * kcA; kcB = -fkB.x * kcB; vc[c][0] = -fvA.x * fvA.y; vc[c][1] = -fvB.x * fvB.y;
+          }
+          kcA *= sm_scale; kcB *= sm_scale;
+          tl[c][0] = fmaf(ksA, sc[c][0] - biasq0, kcA * sumq0);
+          tl[c][1] = fmaf(ksA, sc[c][1] - biasq1, kcA * sumq1);
+          tl[c][2] = fmaf(ksB, sc[c][2] - biasq0, kcB * sumq0);
+          tl[c][3] = fmaf(ksB, sc[c][3] - biasq1, kcB * sumq1);
         }
-        const bool okA = (t0 + tokA) < tlen, okB = (t0 + 8 + tokA) < tlen;
-        const float tA0 = okA ? (ksA * sc0 + kcA * sumq0) * sm_scale : -CUDART_INF_F;
-        const float tA1 = okA ? (ksA * sc1 + kcA * sumq1) * sm_scale : -CUDART_INF_F;
-        const float tB0 = okB ? (ksB * sc2 + kcB * sumq0) * sm_scale : -CUDART_INF_F;
-        const float tB1 = okB ? (ksB * sc3 + kcB * sumq1) * sm_scale : -CUDART_INF_F;
-        float mh0 = fmaxf(tA0, tB0), mh1 = fmaxf(tA1, tB1);
+        if (partial) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (t0 + c * kChunk + tokA >= tlen) tl[c][0] = tl[c][1] = -CUDART_INF_F;
+            if (t0 + c * kChunk + 8 + tokA >= tlen) tl[c][2] = tl[c][3] = -CUDART_INF_F;
+          }
+        }
+        // online softmax with lazy rescale
+        float mh0 = fmaxf(fmaxf(tl[0][0], tl[0][2]), fmaxf(tl[1][0], tl[1][2]));
+        float mh1 = fmaxf(fmaxf(tl[0][1], tl[0][3]), fmaxf(tl[1][1], tl[1][3]));
 #pragma unroll
         for (int m = 4; m <= 16; m <<= 1) {
           mh0 = fmaxf(mh0, __shfl_xor_sync(0xffffffffu, mh0, m));
@@ -394,65 +436,75 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
           const float a0 = n0 ? exp2f(m0 - mh0) : 1.f, a1 = n1 ? exp2f(m1 - mh1) : 1.f;
           if (n0) m0 = mh0;
           if (n1) m1 = mh1;
-          l0 *= a0; cr0 *= a0; l1 *= a1; cr1 *= a1;
+          l0 *= a0; cr0 *= a0; sp0 *= a0; l1 *= a1; cr1 *= a1; sp1 *= a1;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             o[i][0] *= a0; o[i][2] *= a0;
             o[i][1] *= a1; o[i][3] *= a1;
           }
         }
-        const float pA0 = exp2f(tA0 - m0), pA1 = exp2f(tA1 - m1), pB0 = exp2f(tB0 - m0), pB1 = exp2f(tB1 - m1);
-        l0 += pA0 + pB0; l1 += pA1 + pB1;
-        cr0 += pA0 * vcA + pB0 * vcB; cr1 += pA1 * vcA + pB1 * vcB;
-        // P'^T fragments: transpose the (token, head) tiles so that tokens become the MMA k index
-        const uint32_t bp0 = movmatrix_trans(pack_f2h2(pA0 * vsA, pA1 * vsA));  // k = 2q4, 2q4+1  <-> chunk tokens q4, 4+q4
-        const uint32_t bp1 = movmatrix_trans(pack_f2h2(pB0 * vsB, pB1 * vsB));  // k = 2q4+8, +9   <-> chunk tokens 8+q4, 12+q4
-        // ---- O^T += V^T P'^T on raw codes: 8 MMAs (m-tile = 16 dims) ----
-        {
-          const uint8_t* vbase = st + SL::kOffV + (warp * kChunk + q4) * kRow;
+        uint32_t bp[2][2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float pA0 = ex2_approx(tl[c][0] - m0), pA1 = ex2_approx(tl[c][1] - m1);
+          const float pB0 = ex2_approx(tl[c][2] - m0), pB1 = ex2_approx(tl[c][3] - m1);
+          l0 += pA0 + pB0; l1 += pA1 + pB1;
+          cr0 = fmaf(pA0, vc[c][0], fmaf(pB0, vc[c][1], cr0));
+          cr1 = fmaf(pA1, vc[c][0], fmaf(pB1, vc[c][1], cr1));
+          // P' = p * s_v rounded to fp16 (the MMA operand); its exact sum removes the 1024 bias of the V operand afterwards
+          const uint32_t hA = pack_f2h2(pA0 * vs[c][0], pA1 * vs[c][0]), hB = pack_f2h2(pB0 * vs[c][1], pB1 * vs[c][1]);
+          const float2 fA = __half22float2(*reinterpret_cast<const __half2*>(&hA)), fB = __half22float2(*reinterpret_cast<const __half2*>(&hB));
+          sp0 += fA.x + fB.x; sp1 += fA.y + fB.y;
+          // P'^T fragments: transpose the (token, head) tiles so that tokens become the MMA k index
+          bp[c][0] = movmatrix_trans(hA);  // k = 2q4, 2q4+1  <-> chunk tokens q4, 4+q4
+          bp[c][1] = movmatrix_trans(hB);  // k = 2q4+8, +9   <-> chunk tokens 8+q4, 12+q4
+        }
+        // ---- O^T += V^T P'^T on biased codes: 2 x 8 MMAs (m-tile = 16 dims) ----
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint8_t* vbase = st + SL::kOffV + (hbase + c * kChunk + q4) * kRow;
           if constexpr (BITS == 4) {
             const uint2 va = *reinterpret_cast<const uint2*>(vbase + g * 8);
             const uint2 vb = *reinterpret_cast<const uint2*>(vbase + 4 * kRow + g * 8);
-            const uint2 vc = *reinterpret_cast<const uint2*>(vbase + 8 * kRow + g * 8);
+            const uint2 vcw = *reinterpret_cast<const uint2*>(vbase + 8 * kRow + g * 8);
             const uint2 vd = *reinterpret_cast<const uint2*>(vbase + 12 * kRow + g * 8);
 #pragma unroll
             for (int ww = 0; ww < 2; ++ww) {
-              const uint32_t a = ww ? va.y : va.x, bb = ww ? vb.y : vb.x, cc = ww ? vc.y : vc.x, dd = ww ? vd.y : vd.x;
+              const uint32_t a = ww ? va.y : va.x, bb = ww ? vb.y : vb.x, cc = ww ? vcw.y : vcw.x, dd = ww ? vd.y : vd.x;
 #pragma unroll
               for (int kb = 0; kb < 4; ++kb) {
                 const uint32_t sel = static_cast<uint32_t>(kb) | (static_cast<uint32_t>(kb) << 4) | (static_cast<uint32_t>(4 + kb) << 8) |
                                      (static_cast<uint32_t>(4 + kb) << 12);  // bytes [a_kb, a_kb, b_kb, b_kb]
                 const uint32_t m01 = __byte_perm(a, bb, sel), m89 = __byte_perm(cc, dd, sel);
                 const int i = 4 * ww + kb;
-                mma_full(o[i][0], o[i][1], o[i][2], o[i][3], h2_sub(lop3_and_or(m01, 0x000f000fu, kMagic), kMagic),
-                         h2_fma(lop3_and_or(m01, 0x00f000f0u, kMagic), kSixteenth, kNeg64), h2_sub(lop3_and_or(m89, 0x000f000fu, kMagic), kMagic),
-                         h2_fma(lop3_and_or(m89, 0x00f000f0u, kMagic), kSixteenth, kNeg64), bp0, bp1);
+                mma_full(o[i][0], o[i][1], o[i][2], o[i][3], lop3_and_or(m01, 0x000f000fu, kMagic), lop3_and_or(m01, 0x00f000f0u, kMagic),
+                         lop3_and_or(m89, 0x000f000fu, kMagic), lop3_and_or(m89, 0x00f000f0u, kMagic), bp[c][0], bp[c][1]);
               }
             }
           } else {
             const uint4 va = *reinterpret_cast<const uint4*>(vbase + g * 16);
             const uint4 vb = *reinterpret_cast<const uint4*>(vbase + 4 * kRow + g * 16);
-            const uint4 vc = *reinterpret_cast<const uint4*>(vbase + 8 * kRow + g * 16);
+            const uint4 vcw = *reinterpret_cast<const uint4*>(vbase + 8 * kRow + g * 16);
             const uint4 vd = *reinterpret_cast<const uint4*>(vbase + 12 * kRow + g * 16);
             const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-            const uint32_t wc[4] = {vc.x, vc.y, vc.z, vc.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
+            const uint32_t wc[4] = {vcw.x, vcw.y, vcw.z, vcw.w}, wd[4] = {vd.x, vd.y, vd.z, vd.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               // dims 16g + 2i (row g) and 16g + 2i + 1 (row g+8): bytes 2i, 2i+1 of the 16-byte row chunk
               const int w = i >> 1, b0 = 2 * (i & 1), b1 = b0 + 1;
               const uint32_t sel0 = static_cast<uint32_t>(b0) | (static_cast<uint32_t>(b0) << 4) | (static_cast<uint32_t>(4 + b0) << 8) | (static_cast<uint32_t>(4 + b0) << 12);
               const uint32_t sel1 = static_cast<uint32_t>(b1) | (static_cast<uint32_t>(b1) << 4) | (static_cast<uint32_t>(4 + b1) << 8) | (static_cast<uint32_t>(4 + b1) << 12);
-              mma_full(o[i][0], o[i][1], o[i][2], o[i][3], h2_sub(lop3_and_or(__byte_perm(wa[w], wb[w], sel0), 0x00ff00ffu, kMagic), kMagic),
-                       h2_sub(lop3_and_or(__byte_perm(wa[w], wb[w], sel1), 0x00ff00ffu, kMagic), kMagic),
-                       h2_sub(lop3_and_or(__byte_perm(wc[w], wd[w], sel0), 0x00ff00ffu, kMagic), kMagic),
-                       h2_sub(lop3_and_or(__byte_perm(wc[w], wd[w], sel1), 0x00ff00ffu, kMagic), kMagic), bp0, bp1);
+              mma_full(o[i][0], o[i][1], o[i][2], o[i][3], lop3_and_or(__byte_perm(wa[w], wb[w], sel0), 0x00ff00ffu, kMagic),
+                       lop3_and_or(__byte_perm(wa[w], wb[w], sel1), 0x00ff00ffu, kMagic), lop3_and_or(__byte_perm(wc[w], wd[w], sel0), 0x00ff00ffu, kMagic),
+                       lop3_and_or(__byte_perm(wc[w], wd[w], sel1), 0x00ff00ffu, kMagic), bp[c][0], bp[c][1]);
             }
           }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[s]);
-      if (++s == R) { s = 0; ph ^= 1; }
+      s += 2;
+      if (s >= R) { s -= R; ph ^= 1; }
     }
 
     // ---- per-warp partials -> shared memory (the ring is free: every stage of this CTA has been consumed) ----
@@ -463,6 +515,8 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       l1 += __shfl_xor_sync(0xffffffffu, l1, m);
       cr0 += __shfl_xor_sync(0xffffffffu, cr0, m);
       cr1 += __shfl_xor_sync(0xffffffffu, cr1, m);
+      sp0 += __shfl_xor_sync(0xffffffffu, sp0, m);
+      sp1 += __shfl_xor_sync(0xffffffffu, sp1, m);
     }
     if (g == 0) {
       s_m[warp][2 * q4] = m0; s_m[warp][2 * q4 + 1] = m1;
@@ -473,8 +527,10 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       float* so1 = so0 + kD;                                      // head 2q4+1
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        so0[2 * i] = o[i][0] + cr0; so0[2 * i + 1] = o[i][2] + cr0;
-        so1[2 * i] = o[i][1] + cr1; so1[2 * i + 1] = o[i][3] + cr1;
+        // remove the operand bias (1024 sum p'); KV4: the odd dims came from the high nibbles, i.e. 16 x the code
+        constexpr float hs = (BITS == 4) ? 0.0625f : 1.f;
+        so0[2 * i] = (o[i][0] - 1024.f * sp0) + cr0; so0[2 * i + 1] = (o[i][2] - 1024.f * sp0) * hs + cr0;
+        so1[2 * i] = (o[i][1] - 1024.f * sp1) + cr1; so1[2 * i + 1] = (o[i][3] - 1024.f * sp1) * hs + cr1;
       }
     }
     // new token logit: fp32 dot of the rotated, un-quantised q and k  (Template.hpp:1410-1441)
@@ -636,8 +692,8 @@ __global__ void __launch_bounds__(128) prefill_append_kernel(__half* __restrict_
                                                              const int* __restrict__ padding_offset, const long long* __restrict__ kv_pointers,
                                                              int num_tokens, int max_blocks, int num_heads, int num_kv_heads, int seq_len,
                                                              PageGeom pg, float rotary_base, int rotary_dim, int max_positions) {
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int G = num_heads / num_kv_heads;
   const int warps_per_cta = blockDim.x >> 5;
@@ -725,8 +781,8 @@ __global__ void __launch_bounds__(128) prefill_append_kernel(__half* __restrict_
 }
 
 __global__ void padding_offsets_kernel(int* __restrict__ out, const int* __restrict__ cu_seqlens, int max_seqlen) {
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int beg = cu_seqlens[b], end = cu_seqlens[b + 1];
   const int off = b * max_seqlen - beg;

@@ -56,8 +56,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ---------------------------------------------------------------------------------------------
 static __device__ unsigned long long* g_qs_trace = nullptr;
 static __device__ unsigned int g_qs_trace_cap = 0;
-__device__ __forceinline__ void qs_trace(unsigned kernel_id, unsigned phase) {
-  if (g_qs_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+__device__ __forceinline__ void qs_trace(unsigned kernel_id, unsigned phase, unsigned tid = 0) {
+  if (g_qs_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == tid) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
     const unsigned long long i = atomicAdd(g_qs_trace, 1ull);

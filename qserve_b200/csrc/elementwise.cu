@@ -91,9 +91,9 @@ __global__ void __launch_bounds__(kThreads) layernorm_quant_kernel(int8_t* __res
   __shared__ long long red_ll[32];
   const int row = blockIdx.x;
   qs_trace(QS_K_NORM, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_NORM, 1);
-  if (threadIdx.x == 0) pdl_launch_dependents();
   load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
   __syncthreads();
 
@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
   __shared__ long long red_ll[32];
   const int row = blockIdx.x;
   qs_trace(QS_K_ADDNORM, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_ADDNORM, 1);
-  if (threadIdx.x == 0) pdl_launch_dependents();
   {
     const uint4* a = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
     const uint4* b = reinterpret_cast<const uint4*>(delta + static_cast<size_t>(row) * H);
@@ -299,9 +299,9 @@ __global__ void __launch_bounds__(kFusedThreads) silu_mul_quant_kernel(int8_t* _
   const int rank = blockIdx.x - row * csize;
   const int dl = d / csize;  // columns of this CTA (multiple of 8)
   qs_trace(QS_K_SILUQ, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_SILUQ, 1);
-  if (threadIdx.x == 0) pdl_launch_dependents();
   const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + static_cast<size_t>(rank) * dl);
   const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d + static_cast<size_t>(rank) * dl);
   float amax = 0.f;
@@ -371,9 +371,9 @@ __global__ void __launch_bounds__(kThreads) quant_per_token_kernel(int8_t* __res
   __shared__ long long red_ll[32];
   const int row = blockIdx.x;
   qs_trace(QS_K_QUANT, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_QUANT, 1);
-  if (threadIdx.x == 0) pdl_launch_dependents();
   load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
   __syncthreads();
   float amax = 0.f;
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(kThreads) quant_per_token_kernel(int8_t* __res
 }
 
 __global__ void quant_scalar_kernel(int8_t* __restrict__ out, const __half* __restrict__ in, float scale, size_t n) {
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     out[i] = cvt_s8(__fdiv_rn(__half2float(in[i]), scale));
 }
@@ -422,9 +422,9 @@ __global__ void __launch_bounds__(kThreads) rms_norm_kernel(void* __restrict__ o
   __shared__ float red[32];
   const int row = blockIdx.x;
   qs_trace(QS_K_RMS, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_RMS, 1);
-  if (threadIdx.x == 0) pdl_launch_dependents();
   load_row_to_smem(sx, in + static_cast<size_t>(row) * H, H);
   __syncthreads();
   float vs = 0.f;
@@ -470,9 +470,9 @@ __device__ __forceinline__ __half silu_h(__half x) {
 __global__ void __launch_bounds__(kThreads) silu_and_mul_kernel(__half* __restrict__ out, const __half* __restrict__ in, int d) {
   const int row = blockIdx.x;
   qs_trace(QS_K_SILU, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_SILU, 1);
-  if (threadIdx.x == 0) pdl_launch_dependents();
   const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d);
   const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d);
   uint4* go = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * d);
@@ -492,8 +492,8 @@ __global__ void __launch_bounds__(kThreads) silu_and_mul_kernel(__half* __restri
 // legacy exports (not reached by llama_w4a8 / llama_w8a8; API completeness)
 // ------------------------------------------------------------------------------------------------
 __global__ void gelu_kernel(__half* __restrict__ out, const __half* __restrict__ in, size_t n, bool fast) {
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const __half x = in[i];
     __half t;
@@ -514,8 +514,8 @@ __global__ void gelu_kernel(__half* __restrict__ out, const __half* __restrict__
 
 __global__ void dequant_add_residual_kernel(__half* __restrict__ out, const int32_t* __restrict__ in, const __half* __restrict__ residual,
                                             const __half* __restrict__ scale_vec, float scale, int H) {
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const float sc = scale_vec ? __half2float(scale_vec[row]) : scale;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
@@ -525,8 +525,8 @@ __global__ void dequant_add_residual_kernel(__half* __restrict__ out, const int3
 }
 
 __global__ void dequant_kernel(__half* __restrict__ out, const int32_t* __restrict__ in, float scale, int H, int in_stride, int out_stride) {
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   for (int i = threadIdx.x; i < H; i += blockDim.x)
     out[static_cast<size_t>(row) * out_stride + i] = __float2half_rn(__fmul_rn(__int2float_rn(in[static_cast<size_t>(row) * in_stride + i]), scale));
@@ -536,8 +536,8 @@ __global__ void __launch_bounds__(kThreads) dequant_add_residual_rms_norm_quant_
                                                                                       __half* __restrict__ residual, const __half* __restrict__ gamma,
                                                                                       const __half* __restrict__ scale_vec, float scale, float eps, int H) {
   __shared__ float red[32];
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const float sc = scale_vec ? __half2float(scale_vec[row]) : scale;
   float vs = 0.f;
@@ -559,8 +559,8 @@ __global__ void __launch_bounds__(kThreads) dequant_silu_and_mul_quant_kernel(in
                                                                              float scale_gate, float scale_up, float scale_out,
                                                                              float* __restrict__ scale_out_vec, float* __restrict__ tmp) {
   __shared__ float red[32];
-  pdl_wait();
   if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const int32_t* g = in + static_cast<size_t>(row) * 2 * d;
   if (scale_out_vec == nullptr) {

@@ -37,8 +37,9 @@ namespace {
 constexpr int kBM = 128;  // output channels per tile (UMMA M)
 constexpr int kBK = 128;  // K sub-block (= one g128 group, one 128-byte swizzled activation row)
 constexpr int kSub = 2;    // sub-blocks per pipeline stage: per-stage barrier latencies are amortised over 256 K
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kNumThreads = 256;
+// warp roles: 0 weight producer | 1 TMEM owner + MMA issuer | 2..5 unpack + TMEM epilogue | 6 activation producer | 7 spare.
+// All eight warps take part in the final reduce / scale / store phase.
 
 enum { kModeW4Chn = 0, kModeW4Grp = 1, kModeW8 = 2 };
 
@@ -56,33 +57,39 @@ struct GemmParams {
   unsigned long long* prof;  // optional: 16 globaltimer stamps per CTA (tools/gemm_timeline.py)
 };
 
-template <int MODE, int NT, int STAGES>
+// WS = depth of the WEIGHT ring in shared memory.  Weights are static, so the producer streams them before the
+// programmatic-dependent-launch wait: everything that fits in the ring (plus the unpacked stages parked in tensor memory)
+// is already on chip when the preceding activation kernel finishes.
+template <int MODE, int NT, int WS, int AS>
 struct Cfg {
+  static constexpr int kActStages = AS;  // activation ring (L2-resident operand): deep enough to cover the TMA round trip
   static constexpr int kActSub = NT * kBK;                                       // one swizzled [NT x 128 B] activation sub-tile
   static constexpr int kWSub = (MODE == kModeW8) ? kBM * kBK : kBM * kBK / 2;   // int8 rows or packed int4 tiles of one sub-block
   static constexpr int kS2Sub = (MODE == kModeW4Grp) ? 2 * kBM : 0;             // scales | zeros of one group
   static constexpr int kActBytes = kSub * kActSub;
   static constexpr int kWBytes = kSub * kWSub;
   static constexpr int kS2Bytes = kSub * kS2Sub;
-  static constexpr int kStageTx = kActBytes + kWBytes + kS2Bytes;
+  static constexpr int kWStageTx = kWBytes + kS2Bytes;
   static constexpr int kAStageCols = kSub * (kBK / 4);                          // TMEM columns of one unpacked-A stage
-  static constexpr int kACols = (MODE == kModeW8) ? 0 : STAGES * kAStageCols;   // TMEM columns of the unpacked-A ring
-  static constexpr int kTmemNeed = NT + kACols;
+  // unpacked-A ring in tensor memory: as many stages as fit next to the accumulator in 256 (two CTAs / SM) or 512 columns
+  static constexpr int kTA = (MODE == kModeW8) ? 0 : (NT <= 64 ? 3 : NT <= 128 ? 2 : 4);
+  static constexpr int kTmemNeed = NT + kTA * kAStageCols;
   static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   static_assert(kTmemNeed <= 512, "TMEM overflow");
-  // shared memory carve-up (offsets from a 1024-aligned base)
+  // shared memory carve-up (offsets from a 1024-aligned base; activation and W8 weight stages are 1024-byte multiples)
   static constexpr int kOffAct = 0;
-  static constexpr int kOffW = kOffAct + STAGES * kActBytes;
-  static constexpr int kOffS2 = kOffW + STAGES * kWBytes;
-  static constexpr int kPipeBytes = kOffS2 + STAGES * kS2Bytes;
+  static constexpr int kOffW = kOffAct + kActStages * kActBytes;
+  static constexpr int kOffS2 = kOffW + WS * kWBytes;
+  static constexpr int kPipeBytes = kOffS2 + WS * kS2Bytes;
   static constexpr int kRedBytes = NT * kBM * 4;  // INT32 partial tile [NT][128], aliases the pipeline buffers
   static constexpr int kOffRow = (kPipeBytes > kRedBytes ? kPipeBytes : kRedBytes);  // float ascales[NT], asums[NT]
   static constexpr int kOffBar = kOffRow + 2 * NT * 4;
-  static constexpr int kNumBars = 3 * STAGES + 1;
+  static constexpr int kNumBars = 2 * WS + 2 * kActStages + 2 * (kTA > 0 ? kTA : 1) + 1;
   static constexpr int kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr
   static constexpr int kSmemBytes = kOffMisc + 16;
   // two co-resident CTAs per SM when both the TMEM columns (<= 256 each) and the shared memory (<= 113 KB each) allow it
   static constexpr int kCtasPerSm = (kTmemCols <= 256 && kSmemBytes <= 113 * 1024) ? 2 : 1;
+  static_assert(kSmemBytes <= 226 * 1024, "shared memory overflow");
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -127,10 +134,12 @@ __device__ __forceinline__ __half epilogue_one(int32_t acc, float ws, float wsz,
 }
 
 // grid.x = tiles * split; the `split` CTAs of a cluster share one (n_tile, m_tile) and own disjoint K ranges
-template <int MODE, int NT, int STAGES, bool ACC>
-__global__ void __launch_bounds__(kNumThreads, Cfg<MODE, NT, STAGES>::kCtasPerSm)
+template <int MODE, int NT, int WS, int AS, bool ACC>
+__global__ void __launch_bounds__(kNumThreads, Cfg<MODE, NT, WS, AS>::kCtasPerSm)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
-  using C = Cfg<MODE, NT, STAGES>;
+  using C = Cfg<MODE, NT, WS, AS>;
+  constexpr int kActStages = AS;
+  constexpr int TA = C::kTA > 0 ? C::kTA : 1;
   extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts 1024-aligned
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* s_act = smem + C::kOffAct;
@@ -139,10 +148,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   int32_t* s_red = reinterpret_cast<int32_t*>(smem);  // aliases the pipeline buffers once the mainloop has drained
   float* s_asc = reinterpret_cast<float*>(smem + C::kOffRow);
   float* s_asum = s_asc + NT;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
-  uint64_t* bar_afull = bar_full + STAGES;
-  uint64_t* bar_empty = bar_afull + STAGES;
-  uint64_t* bar_dfull = bar_empty + STAGES;
+  uint64_t* bar_wfull = reinterpret_cast<uint64_t*>(smem + C::kOffBar);  // TMA -> unpack warps (W4) / MMA (W8)
+  uint64_t* bar_wempty = bar_wfull + WS;                                   // unpack warps (W4) / MMA commit (W8) -> weight producer
+  uint64_t* bar_xfull = bar_wempty + WS;                                   // activation TMA -> MMA
+  uint64_t* bar_xempty = bar_xfull + kActStages;                           // MMA commit -> activation producer
+  uint64_t* bar_afull = bar_xempty + kActStages;                           // unpack warps -> MMA (TMEM A stage written)
+  uint64_t* bar_aempty = bar_afull + TA;                                   // MMA commit -> unpack warps
+  uint64_t* bar_dfull = bar_aempty + TA;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kOffMisc);
 
   const int warp = threadIdx.x >> 5;
@@ -157,14 +169,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   const int n_kb = kb_end - kb_begin;
   if (threadIdx.x == 0) QS_PROF(0);
   qs_trace(QS_K_GEMM, 0);
+  // final-phase geometry: this thread finishes channel pair `pr` of the tile; its (static) weight scales are fetched now
+  const int npairs = 64 / S;
+  const int pr = (64 * rank) / S + static_cast<int>(threadIdx.x) % npairs;
+  const __half2 ws_h2 = __ldg(reinterpret_cast<const __half2*>(p.wscales + n_tile * kBM + 2 * pr));
+  __half2 wz_h2 = __half2half2(__ushort_as_half(0));
+  if constexpr (MODE == kModeW4Chn) wz_h2 = __ldg(reinterpret_cast<const __half2*>(p.w_szs + n_tile * kBM + 2 * pr));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_act);
     tma_prefetch_desc(&tmap_w);
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&bar_full[i], 1);
+    for (int i = 0; i < WS; ++i) {
+      mbar_init(&bar_wfull[i], 1);
+      mbar_init(&bar_wempty[i], MODE == kModeW8 ? 1 : 4);
+    }
+    for (int i = 0; i < kActStages; ++i) {
+      mbar_init(&bar_xfull[i], 1);
+      mbar_init(&bar_xempty[i], 1);
+    }
+    for (int i = 0; i < TA; ++i) {
       mbar_init(&bar_afull[i], 4);
-      mbar_init(&bar_empty[i], 1);
+      mbar_init(&bar_aempty[i], 1);
     }
     mbar_init(bar_dfull, 1);
     fence_barrier_init();
@@ -177,94 +202,103 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   if (threadIdx.x == 0) { pdl_launch_dependents(); QS_PROF(1); }
 
   if (warp == 0) {
-    // ===================================== TMA producer (one elected lane issues) =====================================
+    // ===================================== weight producer: never waits for the previous kernel =====================================
     if (lane == 0) {
       const int w_row = (MODE == kModeW8) ? n_tile * kBM : n_tile * 4;  // W8: row of [N,K]; W4: band index
-      const int a_row = m_tile * NT;
       const uint8_t* s2s = p.s2_scales + static_cast<size_t>(n_tile) * kBM;
       const uint8_t* s2z = p.s2_zeros + static_cast<size_t>(n_tile) * kBM;
       // one stage = kSub sub-blocks of 128 K.  A sub-block past the end of K (K % 256 == 128) is zero-filled by the
       // tensor maps (weights and activations), so it contributes nothing; its g128 params are re-read from the last group.
-      auto issue_w = [&](int st, int s) {
-        mbar_expect_tx(&bar_full[s], C::kStageTx);
+      int s = 0;
+      uint32_t ph = 0;  // parity of the (it / WS - 1)-th completion of wempty[s]
+      for (int it = 0; it < n_kb; ++it) {
+        if (it >= WS) mbar_wait(&bar_wempty[s], ph);
+        mbar_expect_tx(&bar_wfull[s], C::kWStageTx);
 #pragma unroll
         for (int u = 0; u < kSub; ++u) {
-          const int kb = (kb_begin + st) * kSub + u;
+          const int kb = (kb_begin + it) * kSub + u;
           // W4: u64 elements, 256 per 128-K block of one band (4 tiles x 512 B); W8: bytes
-          tma_load_2d(s_w + s * C::kWBytes + u * C::kWSub, &tmap_w, (MODE == kModeW8) ? kb * kBK : kb * 256, w_row, &bar_full[s]);
+          tma_load_2d(s_w + s * C::kWBytes + u * C::kWSub, &tmap_w, (MODE == kModeW8) ? kb * kBK : kb * 256, w_row, &bar_wfull[s]);
           if constexpr (MODE == kModeW4Grp) {
             const int kg = kb < p.K / kBK ? kb : p.K / kBK - 1;
-            bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub, s2s + static_cast<size_t>(kg) * p.N, kBM, &bar_full[s]);
-            bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub + kBM, s2z + static_cast<size_t>(kg) * p.N, kBM, &bar_full[s]);
+            bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub, s2s + static_cast<size_t>(kg) * p.N, kBM, &bar_wfull[s]);
+            bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub + kBM, s2z + static_cast<size_t>(kg) * p.N, kBM, &bar_wfull[s]);
           }
         }
-      };
-      auto issue_a = [&](int st, int s) {
-#pragma unroll
-        for (int u = 0; u < kSub; ++u)
-          tma_load_2d(s_act + s * C::kActBytes + u * C::kActSub, &tmap_act, ((kb_begin + st) * kSub + u) * kBK, a_row, &bar_full[s]);
-      };
-      // static weights do not depend on the previous kernel: prefetch a full ring before the PDL wait
-      const int pre = n_kb < STAGES ? n_kb : STAGES;
-      for (int it = 0; it < pre; ++it) issue_w(it, it);
-      pdl_wait();
-      QS_PROF(2);
-      qs_trace(QS_K_GEMM, 1);
-      for (int it = 0; it < pre; ++it) issue_a(it, it);
-      int s = 0;
-      uint32_t ph = 0;  // parity of the (it / STAGES - 1)-th completion of empty[s]
-      for (int it = pre; it < n_kb; ++it) {
-        mbar_wait(&bar_empty[s], ph);
-        issue_w(it, s);
-        issue_a(it, s);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (++s == WS) { s = 0; if (it >= WS) ph ^= 1; }
       }
       QS_PROF(3);
+    }
+  } else if (warp == 6) {
+    // ===================================== activation producer =====================================
+    if (lane == 0) {
+      const int a_row = m_tile * NT;
+      pdl_wait();  // the activations are the previous kernel's output
+      QS_PROF(2);
+      qs_trace(QS_K_GEMM, 1, 6 * 32);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_kb; ++it) {
+        if (it >= kActStages) mbar_wait(&bar_xempty[s], ph);
+        mbar_expect_tx(&bar_xfull[s], C::kActBytes);
+#pragma unroll
+        for (int u = 0; u < kSub; ++u)
+          tma_load_2d(s_act + s * C::kActBytes + u * C::kActSub, &tmap_act, ((kb_begin + it) * kSub + u) * kBK, a_row, &bar_xfull[s]);
+        if (++s == kActStages) { s = 0; if (it >= kActStages) ph ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_i8(kBM, NT, 1u, 1u);
-      int s = 0;
-      uint32_t ph = 0;
+      int sw = 0, sx = 0;
+      uint32_t phw = 0, phx = 0;
       for (int it = 0; it < n_kb; ++it) {
-        // W4: the unpack warps observed full[s] before arriving on afull[s], so afull[s] alone orders the TMA data
-        if constexpr (MODE == kModeW8) mbar_wait(&bar_full[s], ph); else mbar_wait(&bar_afull[s], ph);
+        // W4: the unpack warps observed wfull before arriving on afull, so afull alone orders the weight data
+        if constexpr (MODE == kModeW8) mbar_wait(&bar_wfull[sw], phw); else mbar_wait(&bar_afull[sw], phw);
+        mbar_wait(&bar_xfull[sx], phx);
         if (it == 0) QS_PROF(4);
         tc_fence_after();
 #pragma unroll
         for (int u = 0; u < kSub; ++u) {
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + s * C::kActBytes + u * C::kActSub));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + sx * C::kActBytes + u * C::kActSub));
 #pragma unroll
           for (int t = 0; t < kBK / 32; ++t) {
             const uint32_t acc = (it > 0 || u > 0 || t > 0) ? 1u : 0u;
             if constexpr (MODE == kModeW8) {
-              const uint64_t adesc = umma_desc_sw128(smem_u32(s_w + s * C::kWBytes + u * C::kWSub));
+              const uint64_t adesc = umma_desc_sw128(smem_u32(s_w + sw * C::kWBytes + u * C::kWSub));
               umma_i8_ss(tmem_base, adesc + t * 2, bdesc + t * 2, idesc, acc);
             } else {
-              umma_i8_ts(tmem_base, tmem_base + NT + s * C::kAStageCols + u * (kBK / 4) + t * 8, bdesc + t * 2, idesc, acc);
+              umma_i8_ts(tmem_base, tmem_base + NT + sw * C::kAStageCols + u * (kBK / 4) + t * 8, bdesc + t * 2, idesc, acc);
             }
           }
         }
-        umma_commit(&bar_empty[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if constexpr (MODE == kModeW8) umma_commit(&bar_wempty[sw]); else umma_commit(&bar_aempty[sw]);
+        umma_commit(&bar_xempty[sx]);
+        constexpr int RW = (MODE == kModeW8) ? WS : TA;
+        if (++sw == RW) { sw = 0; phw ^= 1; }
+        if (++sx == kActStages) { sx = 0; phx ^= 1; }
       }
       umma_commit(bar_dfull);
       QS_PROF(6);
     }
-  } else {
-    // ===================================== unpack + epilogue warps =====================================
+  } else if (warp >= 2 && warp <= 5) {
+    // ===================================== unpack + TMEM epilogue warps =====================================
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int epi_tid = quad * 32 + lane; // 0..127 == channel row inside the tile
     if constexpr (MODE != kModeW8) {
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, ta = 0;
+      uint32_t ph = 0, pha = 0;  // pha: parity of the (it / TA - 1)-th completion of aempty[ta]
       for (int it = 0; it < n_kb; ++it) {
-        mbar_wait(&bar_full[s], ph);
+        mbar_wait(&bar_wfull[s], ph);
+        if (it >= TA) {
+          mbar_wait(&bar_aempty[ta], pha);
+          tc_fence_after();
+        }
 #pragma unroll
         for (int u = 0; u < kSub; ++u) {
           const uint8_t* wsrc = s_w + s * C::kWBytes + u * C::kWSub + quad * 2048 + lane * 16;
-          const uint32_t tdst = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + NT + s * C::kAStageCols + u * (kBK / 4);
+          const uint32_t tdst = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + NT + ta * C::kAStageCols + u * (kBK / 4);
           uint32_t sc4 = 0, zp4 = 0;
           if constexpr (MODE == kModeW4Grp) {
             const uint8_t* s2 = s_s2 + s * C::kS2Bytes + u * C::kS2Sub + quad * 32 + (lane >> 2) * 4;
@@ -296,15 +330,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_afull[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        if (lane == 0) {
+          mbar_arrive(&bar_afull[ta]);
+          mbar_arrive(&bar_wempty[s]);  // the shared-memory stage has been consumed into registers / tensor memory
+        }
+        if (++s == WS) { s = 0; ph ^= 1; }
+        if (++ta == TA) { ta = 0; if (it >= TA) pha ^= 1; }
       }
     }
 
     // ------------------------------------------ epilogue ------------------------------------------
     pdl_wait();  // ascales / a_ssums / out belong to the dependency chain
     const int m0 = m_tile * NT;
-    for (int j = epi_tid; j < NT; j += kEpiThreads) {
+    for (int j = epi_tid; j < NT; j += 128) {
       const bool ok = (m0 + j) < p.M;
       s_asc[j] = ok ? __half2float(p.ascales[m0 + j]) : 0.f;
       if constexpr (MODE == kModeW4Chn) s_asum[j] = ok ? __half2float(p.a_ssums[m0 + j]) : 0.f;
@@ -324,35 +362,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       for (int i = 0; i < 32; ++i) s_red[(c * 32 + i) * kBM + epi_tid] = static_cast<int32_t>(r[i]);
     }
     if (epi_tid == 0) QS_PROF(9);
+  } else {
+    pdl_wait();  // warp 7 (and the idle lanes' warps reach the barrier below directly): it stores to `out` in the final phase
   }
 
   // ---------------- cross-CTA (cluster) reduction of the INT32 partial tiles through distributed shared memory ----------------
   tc_fence_before();
   if (S > 1) cluster_sync_all(); else __syncthreads();
-  if (warp >= 2) {
-    const int epi_tid = (warp & 3) * 32 + lane;
-    if (epi_tid == 0) QS_PROF(10);
-    // this CTA finishes channel pairs [pair0, pair1) of the tile for all NT tokens
-    const int pair0 = (64 * rank) / S, pair1 = (64 * (rank + 1)) / S;
-    const int npairs = pair1 - pair0;
+  {
+    // all 256 threads: this CTA finishes channel pairs [pair0, pair1) of the tile for all NT tokens
+    pdl_wait();  // already resolved; makes every storing thread an observer of the dependency
+    const int tid = threadIdx.x;
+    if (tid == 0) QS_PROF(10);
     const int m0 = m_tile * NT;
     const uint32_t red_local = smem_u32(s_red);
-    uint32_t red_peer[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) red_peer[r] = (S > 1 && r < S) ? map_to_cta(red_local, r) : red_local;
-    // npairs divides 128, so a thread keeps one channel pair and walks the tokens
-    const int pr = pair0 + epi_tid % npairs;
-    const int tstep = kEpiThreads / npairs;
+    // npairs divides 256, so a thread keeps one channel pair and walks the tokens
+    const int tstep = kNumThreads / npairs;    // 4 * S tokens are finished per pass of the CTA
     const int n = n_tile * kBM + 2 * pr;
-    const __half2 ws = *reinterpret_cast<const __half2*>(p.wscales + n);
     float wz0 = 0.f, wz1 = 0.f;
-    if constexpr (MODE == kModeW4Chn) {
-      const __half2 wz = *reinterpret_cast<const __half2*>(p.w_szs + n);
-      wz0 = __low2float(wz); wz1 = __high2float(wz);
-    }
-    const float ws0 = __low2float(ws), ws1 = __high2float(ws);
+    if constexpr (MODE == kModeW4Chn) { wz0 = __low2float(wz_h2); wz1 = __high2float(wz_h2); }
+    const float ws0 = __low2float(ws_h2), ws1 = __high2float(ws_h2);
     const int tok_end = min(NT, p.M - m0);  // tokens of this tile that exist
-    const int tok0 = epi_tid / npairs;
+    const int tok0 = tid / npairs;
     const uint32_t off0 = static_cast<uint32_t>((tok0 * kBM + 2 * pr) * 4), off_step = static_cast<uint32_t>(tstep * kBM * 4);
     __half* optr = p.out + static_cast<size_t>(m0 + tok0) * p.N + n;
     const size_t ostep = static_cast<size_t>(tstep) * p.N;
@@ -363,32 +394,70 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       *reinterpret_cast<__half2*>(dst) = __halves2half2(o0, o1);
       if constexpr (ACC) *reinterpret_cast<int2*>(p.acc_out + (dst - p.out)) = acc;
     };
+    // tokens per thread: NT / (4 S); every round has 16 (distributed-)shared-memory loads in flight per thread
     if (S == 1) {
-#pragma unroll 4
-      for (int tok = tok0, i = 0; tok < tok_end; tok += tstep, ++i) {
-        const int2 acc = *reinterpret_cast<const int2*>(reinterpret_cast<const uint8_t*>(s_red) + off0 + i * off_step);
-        finish(tok, acc, optr + i * ostep);
+#pragma unroll 1
+      for (int i0 = 0; i0 * tstep + tok0 < NT; i0 += 16) {
+        int2 v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (NT / 4 > e) v[e] = *reinterpret_cast<const int2*>(reinterpret_cast<const uint8_t*>(s_red) + off0 + (i0 + e) * off_step);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int tok = tok0 + (i0 + e) * tstep;
+          if (NT / 4 > e && tok < tok_end) finish(tok, v[e], optr + (i0 + e) * ostep);
+        }
       }
     } else {
-      // two tokens per round: all 2*S distributed-shared-memory loads are issued before any of them is consumed
-      for (int tok = tok0, i = 0; tok < tok_end; tok += 2 * tstep, i += 2) {
-        int2 v[2][8];
+      uint32_t red_peer[8];
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+      for (int r = 0; r < 8; ++r) red_peer[r] = (r < S) ? map_to_cta(red_local, r) : red_local;
+      const int tpt = NT / (4 * S);                 // tokens of this thread
+      const int per_round = S == 2 ? 8 : S == 4 ? 4 : 2;   // 16 / S tokens per round
+      for (int i0 = 0; i0 < tpt; i0 += per_round) {
+        if (S == 2) {
+          int2 v[8][2];
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (r < S) v[e][r] = ld_dsmem_v2(red_peer[r] + off0 + (i + e) * off_step);  // over-read of the 2nd token stays inside s_red
+          for (int e = 0; e < 8; ++e)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          int2 acc = make_int2(0, 0);
+            for (int r = 0; r < 2; ++r) v[e][r] = (i0 + e < tpt) ? ld_dsmem_v2(red_peer[r] + off0 + (i0 + e) * off_step) : make_int2(0, 0);
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (r < S) { acc.x += v[e][r].x; acc.y += v[e][r].y; }
-          if (tok + e * tstep < tok_end) finish(tok + e * tstep, acc, optr + (i + e) * ostep);
+          for (int e = 0; e < 8; ++e) {
+            const int tok = tok0 + (i0 + e) * tstep;
+            if (i0 + e < tpt && tok < tok_end) finish(tok, make_int2(v[e][0].x + v[e][1].x, v[e][0].y + v[e][1].y), optr + (i0 + e) * ostep);
+          }
+        } else if (S == 4) {
+          int2 v[4][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[e][r] = (i0 + e < tpt) ? ld_dsmem_v2(red_peer[r] + off0 + (i0 + e) * off_step) : make_int2(0, 0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int tok = tok0 + (i0 + e) * tstep;
+            int2 acc = make_int2(0, 0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { acc.x += v[e][r].x; acc.y += v[e][r].y; }
+            if (i0 + e < tpt && tok < tok_end) finish(tok, acc, optr + (i0 + e) * ostep);
+          }
+        } else {
+          int2 v[2][8];
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[e][r] = (i0 + e < tpt) ? ld_dsmem_v2(red_peer[r] + off0 + (i0 + e) * off_step) : make_int2(0, 0);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int tok = tok0 + (i0 + e) * tstep;
+            int2 acc = make_int2(0, 0);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { acc.x += v[e][r].x; acc.y += v[e][r].y; }
+            if (i0 + e < tpt && tok < tok_end) finish(tok, acc, optr + (i0 + e) * ostep);
+          }
         }
       }
     }
-    if (epi_tid == 0) QS_PROF(11);
+    if (tid == 0) QS_PROF(11);
   }
   // no CTA may exit (and free its shared memory) while peers are still reading it
   if (S > 1) cluster_sync_all(); else __syncthreads();
@@ -470,9 +539,9 @@ int choose_split(int tiles, int kb_per_tile, int forced) {
   return s;
 }
 
-template <int MODE, int NT, int STAGES>
+template <int MODE, int NT, int WS, int AS>
 int launch_gemm(const GemmArgs& a) {
-  using C = Cfg<MODE, NT, STAGES>;
+  using C = Cfg<MODE, NT, WS, AS>;
   GemmParams p{};
   p.s2_scales = static_cast<const uint8_t*>(a.s2_scales);
   p.s2_zeros = static_cast<const uint8_t*>(a.s2_zeros);
@@ -496,7 +565,7 @@ int launch_gemm(const GemmArgs& a) {
   rc = (MODE == kModeW8) ? make_tmap_u8(&tm_w, a.weight, a.N, a.K, kBM) : make_tmap_w4(&tm_w, a.weight, a.N, a.K);
   if (rc) return rc;
 
-  auto kern = a.acc_out ? gemm_kernel<MODE, NT, STAGES, true> : gemm_kernel<MODE, NT, STAGES, false>;
+  auto kern = a.acc_out ? gemm_kernel<MODE, NT, WS, AS, true> : gemm_kernel<MODE, NT, WS, AS, false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[a.acc_out ? 1 : 0]) {
     rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "cudaFuncSetAttribute(gemm smem)");
@@ -527,11 +596,12 @@ int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.K % kBK == 0, "gemm: K=%d must be a multiple of %d", a.K, kBK);
   QS_REQUIRE((reinterpret_cast<uintptr_t>(a.act) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.weight) & 15) == 0, "gemm: operands must be 16-byte aligned");
   QS_REQUIRE(a.force_split == 0 || a.force_split == 1 || a.force_split == 2 || a.force_split == 4 || a.force_split == 8, "gemm: split must be 1, 2, 4 or 8");
-  // stages are 256 K deep; counts chosen so that NT <= 128 fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns)
-  if (a.M <= 32) return launch_gemm<MODE, 32, (MODE == kModeW8 ? 2 : 3)>(a);
-  if (a.M <= 64) return launch_gemm<MODE, 64, (MODE == kModeW8 ? 2 : 3)>(a);
-  if (a.M <= 128) return launch_gemm<MODE, 128, 2>(a);
-  return launch_gemm<MODE, 256, 2>(a);
+  // weight-ring depths (256-K stages) chosen so that NT <= 128 fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns)
+  constexpr bool w8 = (MODE == kModeW8), grp = (MODE == kModeW4Grp);
+  if (a.M <= 32) return launch_gemm<MODE, 32, (w8 ? 2 : grp ? 4 : 5), 4>(a);
+  if (a.M <= 64) return launch_gemm<MODE, 64, (w8 ? 2 : grp ? 3 : 4), 3>(a);
+  if (a.M <= 128) return launch_gemm<MODE, 128, (w8 ? 4 : 2), 2>(a);
+  return launch_gemm<MODE, 256, (w8 ? 2 : 5), 2>(a);
 }
 
 }  // namespace
