@@ -23,7 +23,6 @@ namespace qs {
 namespace {
 
 constexpr int kD = 128;          // head dim (the reference only instantiates Dh = 128, decoderMaskedMultiheadAttention.cu:352-354)
-constexpr int kAttnThreads = 128;
 constexpr int kWarps = 4;
 constexpr int kChunk = 16;       // tokens per warp iteration
 constexpr int kMaxG = 8;         // query heads per CTA (rows of the m16 tile that carry data)
@@ -35,16 +34,6 @@ struct PageGeom {
 };
 
 // ---- fp16 helpers ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) {
-  uint32_t d;
-  asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d;
-  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t x, uint32_t mask, uint32_t orv) {
   uint32_t d;
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(mask), "r"(orv));  // (x & mask) | orv
@@ -59,33 +48,18 @@ __device__ __forceinline__ uint32_t pack_f2h2(float lo, float hi) {
   return d;
 }
 
+__device__ __forceinline__ unsigned long long attn_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+  return t;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 constexpr uint32_t kMagic = 0x64006400u;      // half2(1024, 1024)
-constexpr uint32_t kSixteenth = 0x2c002c00u;  // half2(1/16)
-constexpr uint32_t kNeg64 = 0xd400d400u;      // half2(-64)
-
-// mma.sync m16n8k16 (fp16 x fp16 -> fp32); rows 8..15 of A are zero (a1 = a3 = 0)
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ uint4 ldg_nc_128(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ uint2 ldg_nc_64(const void* p) {
-  uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
+constexpr uint32_t kOnesH2 = 0x3c003c00u;     // half2(1, 1)
 
 // A4 quantisation parameters (Template.hpp:1243,1067): scale = half((max-min)/L), zero = half(-L*min/(max-min))
 __device__ __forceinline__ void kv_quant_params(float mx, float mn, float L, __half& s, __half& z) {
@@ -112,21 +86,29 @@ __device__ __forceinline__ uint32_t kv_quant_code(float x, float inv_s, float z)
 //   instead of 2 x 128 elements.  (KV8: k_t = s_t * (u_t - z_t), same folding with c_t = -s_t * z_t in fp32.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kAttnConsumers = 128;
-constexpr int kAttnThreadsV2 = kAttnConsumers + 32;
+constexpr int kAttnThreadsV2 = kAttnConsumers;  // no dedicated producer warp: every warp streams its own half pages
 constexpr int kPageTokens = 64;
-constexpr int kMaxBlocksSmem = 160;  // page pointers staged in shared memory (>= 8192 / 64 + slack)
+constexpr int kOStride = kD + 4;  // floats per (warp, head) row of the merge buffer
 
+// One stage = the 32-token slice of one 64-token page of one kv head that a warp consumes in one iteration:
+// K codes | V codes | K scales | K zeros | V scales | V zeros.  Each warp owns a private ring of kStages such slices, filled by
+// its lane 0 with six cp.async.bulk copies and guarded by one "full" mbarrier per slot (the refill of a slot is issued by the
+// same warp right after it has consumed it, so no "empty" barrier and no producer warp are needed).
+constexpr int kSliceTokens = 32;
 template <int BITS>
 struct StageLayout {
-  static constexpr int kCodes = kPageTokens * kD * BITS / 8;  // bytes of K (or V) codes of one head-page
+  static constexpr int kCodes = kPageTokens * kD * BITS / 8;       // bytes of K (or V) codes of one head-page
+  static constexpr int kSliceCodes = kSliceTokens * kD * BITS / 8;  // ... of one 32-token slice
   static constexpr int kOffK = 0;
-  static constexpr int kOffV = kCodes;
-  static constexpr int kOffKs = 2 * kCodes;      // fp16 [64]
-  static constexpr int kOffKz = kOffKs + 128;
-  static constexpr int kOffVs = kOffKz + 128;
-  static constexpr int kOffVz = kOffVs + 128;
-  static constexpr int kBytes = kOffVz + 128;
-  static constexpr int kStages = (BITS == 4) ? 4 : 3;
+  static constexpr int kOffV = kSliceCodes;
+  static constexpr int kOffKs = 2 * kSliceCodes;   // fp16 [32]
+  static constexpr int kOffKz = kOffKs + 64;
+  static constexpr int kOffVs = kOffKz + 64;
+  static constexpr int kOffVz = kOffVs + 64;
+  static constexpr int kBytes = kOffVz + 64;
+  static constexpr int kStages = 2;
+  static constexpr int kWarpBytes = kStages * kBytes;  // private ring of one warp (also holds its partial O^T at the end)
+  static_assert(kWarpBytes >= kMaxG * kOStride * 4, "the per-warp ring must hold the warp's partial output");
 };
 
 // full m16n8k16: all four A registers and all four accumulators carry data
@@ -150,7 +132,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
                         long long k_stride, long long v_stride, const long long* __restrict__ kv_pointers, const int* __restrict__ lengths,
                         __half* __restrict__ out, int num_heads, int num_kv_heads, int max_blocks, PageGeom pg, float rotary_base, int rotary_dim,
                         int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt, uint32_t* __restrict__ tok_cnt, int8_t* __restrict__ q_out,
-                        __half* __restrict__ q_scale, __half* __restrict__ q_sum) {
+                        __half* __restrict__ q_scale, __half* __restrict__ q_sum, unsigned long long* __restrict__ prof) {
   using SL = StageLayout<BITS>;
   constexpr int R = SL::kStages;
   const int G = num_heads / num_kv_heads;
@@ -165,29 +147,27 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
   const int g = lane >> 2, q4 = lane & 3;
 
   extern __shared__ __align__(128) uint8_t smem_attn[];
-  uint8_t* s_ring = smem_attn;                                           // R stages
-  float* s_o = reinterpret_cast<float*>(smem_attn);                      // merge buffer [4][8][128], aliases the ring at the end
+  uint8_t* s_ring = smem_attn;                                           // kWarps private rings of R slices
   __shared__ __align__(16) __half s_q[kMaxG * kD];
   __shared__ __align__(16) __half s_k[kD];
   __shared__ __align__(16) __half s_v[kD];
-  __shared__ float s_cs[kD];
   __shared__ float s_m[kWarps + 1][kMaxG], s_l[kWarps + 1][kMaxG];
-  __shared__ long long s_kp[kMaxBlocksSmem], s_vp[kMaxBlocksSmem];
-  __shared__ uint32_t s_meta[R][2][kPageTokens];                         // per token packed (s, c) for K and V
-  __shared__ __align__(8) uint64_t s_full[R], s_empty[R];
+  __shared__ float s_f[kWarps + 1][kMaxG];                                // merge weights exp2(m_w - M) [* 1 / L]
+  __shared__ float2 s_meta[kWarps][2][kSliceTokens];                     // per token (scale, c) of the slice in flight: K pre-multiplied by sm_scale
+  __shared__ __align__(8) uint64_t s_full[kWarps][R];
   __shared__ uint32_t s_last;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < R; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 2);  // the two consumer warps that share a page
-    }
+    for (int i = 0; i < kWarps * R; ++i) mbar_init(&s_full[0][0] + i, 1);
     fence_barrier_init();
   }
+#define ATTN_PROF(slot) do { if (prof) prof[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = attn_gtime(); } while (0)
+  if (threadIdx.x == 0) ATTN_PROF(0);
   qs_trace(QS_K_ATTN, 0);
   if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
   pdl_wait();
   qs_trace(QS_K_ATTN, 1);
+  if (threadIdx.x == 0) ATTN_PROF(1);
 
   const int tlen = (lengths ? lengths[b] : timestep) - 1;  // tokens already in the cache (Template.hpp:901)
   const long long* kptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 0) * max_blocks;
@@ -196,66 +176,86 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
   const int pps = (n_pages + nsplit - 1) / nsplit;
   const int p_begin = split * pps, p_end = min(n_pages, p_begin + pps);
   const int last_blk = tlen / pg.tokens_per_block;  // page receiving the new token
-  for (int i = threadIdx.x; i <= last_blk && i < kMaxBlocksSmem; i += kAttnThreadsV2) {
-    s_kp[i] = kptrs[i];
-    s_vp[i] = vptrs[i];
-  }
-  __syncthreads();
 
-  if (warp == kWarps) {
-    // ================================ producer warp: stream this split's pages ================================
+  // ---- this warp's stream: token slice [32 (warp & 1), +32) of the pages p_begin + (warp >> 1), +2, ...  ----
+  const int hslice = warp & 1;
+  const int my_first = p_begin + (warp >> 1);
+  const int n_my = (p_end > my_first) ? (p_end - my_first + 1) / 2 : 0;
+  uint8_t* my_ring = s_ring + warp * SL::kWarpBytes;
+  uint64_t* my_full = &s_full[warp][0];
+  const int zoff = pg.num_kv_heads * pg.tokens_per_block * 2;  // bytes from a scale row to the zero row
+  long long kp_l = 0, vp_l = 0;  // lane l: page pointers of this warp's page (batch * 32 + l)
+  auto load_ptr_batch = [&](int j0) {
+    const int pidx = my_first + 2 * (j0 + lane);
+    kp_l = (pidx < p_end) ? kptrs[pidx] : 0;
+    vp_l = (pidx < p_end) ? vptrs[pidx] : 0;
+  };
+  auto issue = [&](int j, int slot) {  // all lanes call; lane 0 issues the six copies of this warp's j-th slice into `slot`
+    const long long kp_j = __shfl_sync(0xffffffffu, kp_l, j & 31), vp_j = __shfl_sync(0xffffffffu, vp_l, j & 31);
     if (lane == 0) {
-      const int zoff = pg.num_kv_heads * pg.tokens_per_block * 2;  // bytes from a scale row to the zero row
-      int s = 0;
-      uint32_t ph = 0;
-      for (int pidx = p_begin; pidx < p_end; ++pidx) {
-        if (pidx - p_begin >= R) mbar_wait(&s_empty[s], ph ^ 1);
-        const uint8_t* kpage = reinterpret_cast<const uint8_t*>(s_kp[pidx]);
-        const uint8_t* vpage = reinterpret_cast<const uint8_t*>(s_vp[pidx]);
-        uint8_t* dst = s_ring + s * SL::kBytes;
-        mbar_expect_tx(&s_full[s], SL::kBytes);
-        bulk_copy_g2s(dst + SL::kOffK, kpage + static_cast<size_t>(hk) * SL::kCodes, SL::kCodes, &s_full[s]);
-        bulk_copy_g2s(dst + SL::kOffV, vpage + static_cast<size_t>(hk) * SL::kCodes, SL::kCodes, &s_full[s]);
-        const uint8_t* kmeta = kpage + pg.code_bytes + hk * 128;
-        const uint8_t* vmeta = vpage + pg.code_bytes + hk * 128;
-        bulk_copy_g2s(dst + SL::kOffKs, kmeta, 128, &s_full[s]);
-        bulk_copy_g2s(dst + SL::kOffKz, kmeta + zoff, 128, &s_full[s]);
-        bulk_copy_g2s(dst + SL::kOffVs, vmeta, 128, &s_full[s]);
-        bulk_copy_g2s(dst + SL::kOffVz, vmeta + zoff, 128, &s_full[s]);
-        if (++s == R) { s = 0; ph ^= 1; }
-      }
+      const uint8_t* kpage = reinterpret_cast<const uint8_t*>(kp_j);
+      const uint8_t* vpage = reinterpret_cast<const uint8_t*>(vp_j);
+      uint8_t* dst = my_ring + slot * SL::kBytes;
+      fence_proxy_async();  // the slot was last read through the generic proxy
+      mbar_expect_tx(&my_full[slot], SL::kBytes);
+      bulk_copy_g2s(dst + SL::kOffK, kpage + static_cast<size_t>(hk) * SL::kCodes + hslice * SL::kSliceCodes, SL::kSliceCodes, &my_full[slot]);
+      bulk_copy_g2s(dst + SL::kOffV, vpage + static_cast<size_t>(hk) * SL::kCodes + hslice * SL::kSliceCodes, SL::kSliceCodes, &my_full[slot]);
+      const uint8_t* kmeta = kpage + pg.code_bytes + hk * 128 + hslice * 64;
+      const uint8_t* vmeta = vpage + pg.code_bytes + hk * 128 + hslice * 64;
+      bulk_copy_g2s(dst + SL::kOffKs, kmeta, 64, &my_full[slot]);
+      bulk_copy_g2s(dst + SL::kOffKz, kmeta + zoff, 64, &my_full[slot]);
+      bulk_copy_g2s(dst + SL::kOffVs, vmeta, 64, &my_full[slot]);
+      bulk_copy_g2s(dst + SL::kOffVz, vmeta + zoff, 64, &my_full[slot]);
     }
-  } else {
+  };
+  load_ptr_batch(0);
+  for (int j = 0; j < R && j < n_my; ++j) issue(j, j);  // the cache stream starts before the new-token work below
+  if (threadIdx.x == 0) ATTN_PROF(3);
+  {
     // ================================ consumer warps ================================
-    // ---- new token: RoPE (NeoX, position tlen) of q and k; stage q, k, v in shared memory ----
-    const int half_rot = rotary_dim / 2;
-    if (threadIdx.x < half_rot) {
-      const float inv_freq = __fdiv_rn(static_cast<float>(tlen), powf(rotary_base, __fdiv_rn(static_cast<float>(2 * threadIdx.x), static_cast<float>(rotary_dim))));
-      float sn, cs;
-      sincosf(inv_freq, &sn, &cs);
-      s_cs[threadIdx.x] = cs;
-      s_cs[half_rot + threadIdx.x] = sn;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ---- new token: RoPE (NeoX, position tlen) of q and k; stage q, k, v in shared memory.
+    //      Thread t rotates the pair (i, i + 64), i = t % 64, of rows t / 64, t / 64 + 2, ... (row Gc is k): the global loads
+    //      go out first, the cos / sin of its own pair is computed while they are in flight (no table, no extra barrier) ----
+    const int half_rot = rotary_dim / 2;  // == 64 (checked on the host)
+    const int ri = threadIdx.x & 63, r0 = threadIdx.x >> 6;
     const __half* kg = k_in + static_cast<size_t>(b) * k_stride + static_cast<size_t>(hk) * kD;
     const __half* vg = v_in + static_cast<size_t>(b) * v_stride + static_cast<size_t>(hk) * kD;
-    for (int idx = threadIdx.x; idx < (Gc + 1) * (kD / 2); idx += kAttnConsumers) {
-      const int r = idx / (kD / 2), i = idx - r * (kD / 2);  // r == Gc -> the k row
-      const __half* src = (r < Gc) ? (q_in + static_cast<size_t>(b) * q_stride + static_cast<size_t>(h0 + r) * kD) : kg;
-      __half* dst = (r < Gc) ? (s_q + r * kD) : s_k;
-      const float x0 = __half2float(src[i]), x1 = __half2float(src[i + half_rot]);
-      const float c = s_cs[i], s = s_cs[half_rot + i];
-      dst[i] = __float2half_rn(__fsub_rn(__fmul_rn(c, x0), __fmul_rn(s, x1)));
-      dst[i + half_rot] = __float2half_rn(__fadd_rn(__fmul_rn(c, x1), __fmul_rn(s, x0)));
+    constexpr int kRowsPerThread = (kMaxG + 2) / 2;
+    __half x0[kRowsPerThread], x1[kRowsPerThread];
+#pragma unroll
+    for (int e = 0; e < kRowsPerThread; ++e) {
+      const int r = r0 + 2 * e;
+      if (r <= Gc) {
+        const __half* src = (r < Gc) ? (q_in + static_cast<size_t>(b) * q_stride + static_cast<size_t>(h0 + r) * kD) : kg;
+        x0[e] = src[ri];
+        x1[e] = src[ri + half_rot];
+      }
     }
-    for (int i = threadIdx.x; i < kD; i += kAttnConsumers) s_v[i] = vg[i];
+    const __half vnew = vg[threadIdx.x];
+    float sn, cs;
+    {
+      const float inv_freq = __fdiv_rn(static_cast<float>(tlen), powf(rotary_base, __fdiv_rn(static_cast<float>(2 * ri), static_cast<float>(rotary_dim))));
+      sincosf(inv_freq, &sn, &cs);
+    }
+#pragma unroll
+    for (int e = 0; e < kRowsPerThread; ++e) {
+      const int r = r0 + 2 * e;
+      if (r <= Gc) {
+        __half* dst = (r < Gc) ? (s_q + r * kD) : s_k;
+        const float f0 = __half2float(x0[e]), f1 = __half2float(x1[e]);
+        dst[ri] = __float2half_rn(__fsub_rn(__fmul_rn(cs, f0), __fmul_rn(sn, f1)));
+        dst[ri + half_rot] = __float2half_rn(__fadd_rn(__fmul_rn(cs, f1), __fmul_rn(sn, f0)));
+      }
+    }
+    s_v[threadIdx.x] = vnew;
     for (int i = threadIdx.x + Gc * kD; i < kMaxG * kD; i += kAttnConsumers) s_q[i] = __float2half_rn(0.f);
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
     // ---- quantise + append the new K / V (one CTA per kv head) ----
     const bool owner_w = (split == 0) && (gpart == 0);
-    if (owner_w && warp < 2) {
-      const __half* src = (warp == 0) ? s_k : s_v;
+    if (owner_w && warp >= 2) {  // warps 2, 3: the first two warps start the main loop one page earlier
+      const bool is_k = (warp == 2);
+      const __half* src = is_k ? s_k : s_v;
       const float L = (BITS == 4) ? 15.f : 255.f;
       float x[4];
 #pragma unroll
@@ -270,7 +270,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       kv_quant_params(mx, mn, L, sc, zp);
       const float inv_s = __fdiv_rn(1.0f, __half2float(sc)), zf = __half2float(zp);
       const int slot = tlen - last_blk * pg.tokens_per_block;
-      uint8_t* page = reinterpret_cast<uint8_t*>((warp == 0) ? kptrs[last_blk] : vptrs[last_blk]);
+      uint8_t* page = reinterpret_cast<uint8_t*>(is_k ? kptrs[last_blk] : vptrs[last_blk]);
       uint32_t c[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) c[j] = kv_quant_code(x[j], inv_s, zf);
@@ -295,13 +295,22 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
     //   sum_d (1024 + w_d u_d) q'_d = B(q) + sum_d u_d q_d ,   B(q) = 1024 sum_{low} q_d + 64 sum_{high} q_d
     float biasq0, biasq1;
     {
-      const __half* qr = s_q + g * kD + 32 * q4;
-      float acc_e = 0.f, acc_o = 0.f;
+      // this thread's 32 q values (head g, dims 32 q4 ..): word k holds dims (2k, 2k+1)
+      uint32_t qw[16];
+      const uint4* qv = reinterpret_cast<const uint4*>(s_q + g * kD + 32 * q4);
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        acc_e += __half2float(qr[j]);
-        acc_o += __half2float(qr[j + 1]);
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const uint4 t = qv[k4];
+        qw[4 * k4] = t.x; qw[4 * k4 + 1] = t.y; qw[4 * k4 + 2] = t.z; qw[4 * k4 + 3] = t.w;
       }
+      float ae[2] = {0.f, 0.f}, ao[2] = {0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qw[k]));
+        ae[k & 1] += f.x;
+        ao[k & 1] += f.y;
+      }
+      float acc_e = ae[0] + ae[1], acc_o = ao[0] + ao[1];
       acc_e += __shfl_xor_sync(0xffffffffu, acc_e, 1);
       acc_o += __shfl_xor_sync(0xffffffffu, acc_o, 1);
       acc_e += __shfl_xor_sync(0xffffffffu, acc_e, 2);
@@ -312,16 +321,18 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       sumq1 = __shfl_sync(0xffffffffu, acc, (2 * q4 + 1) * 4);
       biasq0 = __shfl_sync(0xffffffffu, bias, (2 * q4) * 4);
       biasq1 = __shfl_sync(0xffffffffu, bias, (2 * q4 + 1) * 4);
-      const __half sixteenth = __float2half_rn(0.0625f);
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
         if constexpr (BITS == 4) {
-          const int d0 = 8 * (s >> 1) + 2 * (s & 1);  // k-step 2w: nibbles (0,4 | 1,5); 2w+1: (2,6 | 3,7) of word w
-          qb0[s] = pack_h2(qr[d0], qr[d0 + 4]);
-          qb1[s] = pack_h2(__hmul(qr[d0 + 1], sixteenth), __hmul(qr[d0 + 5], sixteenth));  // exact: a power of two
+          // k-step 2w: nibbles (0,4 | 1,5); 2w+1: (2,6 | 3,7) of word w  ->  dims d0, d0+4 | d0+1, d0+5 with d0 = 8 (s>>1) + 2 (s&1)
+          const int k0 = 4 * (s >> 1) + (s & 1);
+          qb0[s] = __byte_perm(qw[k0], qw[k0 + 2], 0x5410);
+          const uint32_t hi = __byte_perm(qw[k0], qw[k0 + 2], 0x7632);
+          const __half2 sc16 = __hmul2(*reinterpret_cast<const __half2*>(&hi), __float2half2_rn(0.0625f));  // exact: a power of two
+          qb1[s] = *reinterpret_cast<const uint32_t*>(&sc16);
         } else {
-          qb0[s] = pack_h2(qr[4 * s], qr[4 * s + 1]);
-          qb1[s] = pack_h2(qr[4 * s + 2], qr[4 * s + 3]);
+          qb0[s] = qw[2 * s];
+          qb1[s] = qw[2 * s + 1];
         }
       }
     }
@@ -332,37 +343,47 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     // running max, sum p, sum p*c (zero-point correction), sum p' (bias correction of the V operand) per head
-    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f, cr0 = 0.f, cr1 = 0.f, sp0 = 0.f, sp1 = 0.f;
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f, cr0 = 0.f, cr1 = 0.f;
+    float spa[4] = {0.f, 0.f, 0.f, 0.f};  // [0], [1]: sum p' of heads 2q4, 2q4+1 over ALL tokens this warp has seen
 
     // S^T = K Q^T: A rows g / g+8 <-> chunk tokens tokA / 8+tokA (the permutation keeps the V row reads at a 2-way conflict)
     const int tokA = (g & 1) * 4 + (g >> 1);
     constexpr int kRow = kD * BITS / 8;  // bytes per token row
     // warp w consumes tokens [32 (w & 1), +32) of the pages whose index has parity (w >> 1): two 16-token MMA chunks per
     // iteration share one barrier wait, one max reduction and one set of address computations
-    const int hbase = (warp & 1) * 2 * kChunk;
-    int s = warp >> 1;
+    const int hbase = hslice * kSliceTokens;
+    int s = 0;
     uint32_t ph = 0;
-    for (int pidx = p_begin + (warp >> 1); pidx < p_end; pidx += 2) {
-      mbar_wait(&s_full[s], ph);
-      const uint8_t* st = s_ring + s * SL::kBytes;
+    if (threadIdx.x == 0) ATTN_PROF(4);
+    for (int j = 0; j < n_my; ++j) {
+      const int pidx = my_first + 2 * j;
+      mbar_wait(&my_full[s], ph);
+      if (threadIdx.x == 0 && j == 0) ATTN_PROF(5);
+      const uint8_t* st = my_ring + s * SL::kBytes;
       const int t0 = pidx * kPageTokens + hbase;  // first token of this warp's 32-token slice
       if (t0 < tlen) {
-        // per-token (scale, aux) pairs of the 32 K and 32 V tokens
+        // per-token (scale, c = -scale * zero) pairs of the 32 K and 32 V tokens, converted to fp32 ONCE per token here
+        // (fp16 -> fp32 conversions run on the slow XU pipe: the logit code below must not repeat them per thread)
         {
-          const __half* kp = reinterpret_cast<const __half*>(st + SL::kOffKs) + hbase + lane;
-          const __half* vp = reinterpret_cast<const __half*>(st + SL::kOffVs) + hbase + lane;
-          const __half ksc = kp[0], kzp = kp[64], vsc = vp[0], vzp = vp[64];
-          uint32_t pk, pv;
+          const __half* kp = reinterpret_cast<const __half*>(st + SL::kOffKs) + lane;
+          const __half* vp = reinterpret_cast<const __half*>(st + SL::kOffVs) + lane;
+          const __half ksc = kp[0], kzp = kp[32], vsc = vp[0], vzp = vp[32];
+          float2 fk, fv;
           if constexpr (BITS == 4) {
-            pk = pack_h2(ksc, __float2half_rn(__fmul_rn(-__half2float(ksc), __half2float(kzp))));
-            pv = pack_h2(vsc, __float2half_rn(__fmul_rn(-__half2float(vsc), __half2float(vzp))));
+            // c = half(-s * z): the fp16 product of two fp16 values, rounded once
+            fk = __half22float2(__halves2half2(ksc, __hmul(__hneg(ksc), kzp)));
+            fv = __half22float2(__halves2half2(vsc, __hmul(__hneg(vsc), vzp)));
           } else {
-            pk = pack_h2(ksc, kzp);
-            pv = pack_h2(vsc, vzp);
+            fk = __half22float2(__halves2half2(ksc, kzp));
+            fv = __half22float2(__halves2half2(vsc, vzp));
+            fk.y = -fk.x * fk.y;  // aux holds the zero point: c = -s * z in fp32
+            fv.y = -fv.x * fv.y;
           }
-          if (t0 + lane >= tlen) pk = pv = 0u;  // unwritten slots: force finite zeros (their logits are masked below)
-          s_meta[s][0][hbase + lane] = pk;
-          s_meta[s][1][hbase + lane] = pv;
+          fk.x *= sm_scale;
+          fk.y *= sm_scale;
+          if (t0 + lane >= tlen) fk = fv = make_float2(0.f, 0.f);  // unwritten slots: force finite zeros (their logits are masked below)
+          s_meta[warp][0][lane] = fk;
+          s_meta[warp][1][lane] = fv;
         }
         __syncwarp();
         // ---- S^T (2 x 16 tokens x 8 heads) on biased codes: 16 MMAs ----
@@ -370,7 +391,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           sc[c][0] = sc[c][1] = sc[c][2] = sc[c][3] = 0.f;
-          const uint8_t* krow = st + SL::kOffK + (hbase + c * kChunk + tokA) * kRow;
+          const uint8_t* krow = st + SL::kOffK + (c * kChunk + tokA) * kRow;
           if constexpr (BITS == 4) {
             const uint4 ka = *reinterpret_cast<const uint4*>(krow + q4 * 16);
             const uint4 kb = *reinterpret_cast<const uint4*>(krow + 8 * kRow + q4 * 16);
@@ -401,20 +422,13 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
         const bool partial = (t0 + 2 * kChunk > tlen);  // only the last page of a sequence
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const uint32_t mkA = s_meta[s][0][hbase + c * kChunk + tokA], mkB = s_meta[s][0][hbase + c * kChunk + 8 + tokA];
-          const uint32_t mvA = s_meta[s][1][hbase + c * kChunk + tokA], mvB = s_meta[s][1][hbase + c * kChunk + 8 + tokA];
-          const float2 fkA = __half22float2(*reinterpret_cast<const __half2*>(&mkA)), fkB = __half22float2(*reinterpret_cast<const __half2*>(&mkB));
-          const float2 fvA = __half22float2(*reinterpret_cast<const __half2*>(&mvA)), fvB = __half22float2(*reinterpret_cast<const __half2*>(&mvB));
-          float ksA = fkA.x * sm_scale, ksB = fkB.x * sm_scale, kcA = fkA.y, kcB = fkB.y;
+          const float2 fkA = s_meta[warp][0][c * kChunk + tokA], fkB = s_meta[warp][0][c * kChunk + 8 + tokA];
+          const float2 fvA = s_meta[warp][1][c * kChunk + tokA], fvB = s_meta[warp][1][c * kChunk + 8 + tokA];
           vs[c][0] = fvA.x; vs[c][1] = fvB.x; vc[c][0] = fvA.y; vc[c][1] = fvB.y;
-          if constexpr (BITS == 8) {  // aux holds the zero point: c = -s * z
-            kcA = -fkA.x * kcA; kcB = -fkB.x * kcB; vc[c][0] = -fvA.x * fvA.y; vc[c][1] = -fvB.x * fvB.y;
-          }
-          kcA *= sm_scale; kcB *= sm_scale;
-          tl[c][0] = fmaf(ksA, sc[c][0] - biasq0, kcA * sumq0);
-          tl[c][1] = fmaf(ksA, sc[c][1] - biasq1, kcA * sumq1);
-          tl[c][2] = fmaf(ksB, sc[c][2] - biasq0, kcB * sumq0);
-          tl[c][3] = fmaf(ksB, sc[c][3] - biasq1, kcB * sumq1);
+          tl[c][0] = fmaf(fkA.x, sc[c][0] - biasq0, fkA.y * sumq0);
+          tl[c][1] = fmaf(fkA.x, sc[c][1] - biasq1, fkA.y * sumq1);
+          tl[c][2] = fmaf(fkB.x, sc[c][2] - biasq0, fkB.y * sumq0);
+          tl[c][3] = fmaf(fkB.x, sc[c][3] - biasq1, fkB.y * sumq1);
         }
         if (partial) {
 #pragma unroll
@@ -436,7 +450,8 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
           const float a0 = n0 ? exp2f(m0 - mh0) : 1.f, a1 = n1 ? exp2f(m1 - mh1) : 1.f;
           if (n0) m0 = mh0;
           if (n1) m1 = mh1;
-          l0 *= a0; cr0 *= a0; sp0 *= a0; l1 *= a1; cr1 *= a1; sp1 *= a1;
+          l0 *= a0; cr0 *= a0; l1 *= a1; cr1 *= a1;
+          spa[0] *= a0; spa[2] *= a0; spa[1] *= a1; spa[3] *= a1;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             o[i][0] *= a0; o[i][2] *= a0;
@@ -453,16 +468,16 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
           cr1 = fmaf(pA1, vc[c][0], fmaf(pB1, vc[c][1], cr1));
           // P' = p * s_v rounded to fp16 (the MMA operand); its exact sum removes the 1024 bias of the V operand afterwards
           const uint32_t hA = pack_f2h2(pA0 * vs[c][0], pA1 * vs[c][0]), hB = pack_f2h2(pB0 * vs[c][1], pB1 * vs[c][1]);
-          const float2 fA = __half22float2(*reinterpret_cast<const __half2*>(&hA)), fB = __half22float2(*reinterpret_cast<const __half2*>(&hB));
-          sp0 += fA.x + fB.x; sp1 += fA.y + fB.y;
           // P'^T fragments: transpose the (token, head) tiles so that tokens become the MMA k index
           bp[c][0] = movmatrix_trans(hA);  // k = 2q4, 2q4+1  <-> chunk tokens q4, 4+q4
           bp[c][1] = movmatrix_trans(hB);  // k = 2q4+8, +9   <-> chunk tokens 8+q4, 12+q4
+          // sum_t p'_t per head, from the very operand the V MMAs consume: an all-ones A tile (every output row is the sum)
+          mma_full(spa[0], spa[1], spa[2], spa[3], kOnesH2, kOnesH2, kOnesH2, kOnesH2, bp[c][0], bp[c][1]);
         }
         // ---- O^T += V^T P'^T on biased codes: 2 x 8 MMAs (m-tile = 16 dims) ----
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const uint8_t* vbase = st + SL::kOffV + (hbase + c * kChunk + q4) * kRow;
+          const uint8_t* vbase = st + SL::kOffV + (c * kChunk + q4) * kRow;
           if constexpr (BITS == 4) {
             const uint2 va = *reinterpret_cast<const uint2*>(vbase + g * 8);
             const uint2 vb = *reinterpret_cast<const uint2*>(vbase + 4 * kRow + g * 8);
@@ -502,35 +517,40 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
-      s += 2;
-      if (s >= R) { s -= R; ph ^= 1; }
+      // refill the slot just consumed with the slice R iterations ahead
+      if (j + R < n_my) {
+        if (((j + R) & 31) == 0) load_ptr_batch(j + R);
+        issue(j + R, s);
+      }
+      if (++s == R) { s = 0; ph ^= 1; }
     }
 
-    // ---- per-warp partials -> shared memory (the ring is free: every stage of this CTA has been consumed) ----
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 0) ATTN_PROF(6);
+    // ---- per-warp partials -> the warp's own (drained) ring: no need to wait for the other warps ----
 #pragma unroll
     for (int m = 4; m <= 16; m <<= 1) {
       l0 += __shfl_xor_sync(0xffffffffu, l0, m);
       l1 += __shfl_xor_sync(0xffffffffu, l1, m);
       cr0 += __shfl_xor_sync(0xffffffffu, cr0, m);
       cr1 += __shfl_xor_sync(0xffffffffu, cr1, m);
-      sp0 += __shfl_xor_sync(0xffffffffu, sp0, m);
-      sp1 += __shfl_xor_sync(0xffffffffu, sp1, m);
     }
     if (g == 0) {
       s_m[warp][2 * q4] = m0; s_m[warp][2 * q4 + 1] = m1;
       s_l[warp][2 * q4] = l0; s_l[warp][2 * q4 + 1] = l1;
     }
     {
-      float* so0 = s_o + (warp * kMaxG + 2 * q4) * kD + 16 * g;  // head 2q4, dims 16g..16g+15
-      float* so1 = so0 + kD;                                      // head 2q4+1
+      // layout [warp][head][(d % 16) * 8 + d / 16] with a head stride of 132 floats: conflict-free for these stores and for the
+      // merge reads below (thread t owns dim 16 (t % 8) + t / 8)
+      __syncwarp();  // every lane is done with the ring slots this overwrites
+      float* so0 = reinterpret_cast<float*>(my_ring) + (2 * q4) * kOStride + g;  // head 2q4, dims 16g + j at offset 8 j
+      float* so1 = so0 + kOStride;                                // head 2q4+1
+      constexpr float hs = (BITS == 4) ? 0.0625f : 1.f;
+      const float b0 = 1024.f * spa[0], b1 = 1024.f * spa[1];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         // remove the operand bias (1024 sum p'); KV4: the odd dims came from the high nibbles, i.e. 16 x the code
-        constexpr float hs = (BITS == 4) ? 0.0625f : 1.f;
-        so0[2 * i] = (o[i][0] - 1024.f * sp0) + cr0; so0[2 * i + 1] = (o[i][2] - 1024.f * sp0) * hs + cr0;
-        so1[2 * i] = (o[i][1] - 1024.f * sp1) + cr1; so1[2 * i + 1] = (o[i][3] - 1024.f * sp1) * hs + cr1;
+        so0[8 * (2 * i)] = (o[i][0] - b0) + cr0; so0[8 * (2 * i + 1)] = (o[i][2] - b0) * hs + cr0;
+        so1[8 * (2 * i)] = (o[i][1] - b1) + cr1; so1[8 * (2 * i + 1)] = (o[i][3] - b1) * hs + cr1;
       }
     }
     // new token logit: fp32 dot of the rotated, un-quantised q and k  (Template.hpp:1410-1441)
@@ -549,45 +569,57 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) ATTN_PROF(7);
 
-  // ---------------- merge the warps (and the un-quantised new token); one output dim per thread ----------------
+  // ---------------- merge the warps (and the un-quantised new token) ----------------
   const bool owner = (split == 0);
+  const int nparts = kWarps + (owner ? 1 : 0);
+  if (threadIdx.x < kMaxG) {
+    // one thread per head: weights exp2(m_w - M), normalised by 1 / (sum + 1e-6) when this CTA produces the final output
+    const int r = threadIdx.x;
+    float M = -CUDART_INF_F;
+    for (int w = 0; w < nparts; ++w) M = fmaxf(M, s_m[w][r]);
+    float e[kWarps + 1], L = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps + 1; ++w) {
+      e[w] = (w < nparts && s_m[w][r] != -CUDART_INF_F) ? exp2f(s_m[w][r] - M) : 0.f;
+      if (w < nparts) L += s_l[w][r] * e[w];
+    }
+    // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
+    const float inv = (nsplit == 1) ? __fdividef(1.f, L + 1.e-6f) : 1.f;
+#pragma unroll
+    for (int w = 0; w < kWarps + 1; ++w) s_f[w][r] = e[w] * inv;
+    s_m[0][r] = M;   // only read back by the split path below
+    s_l[0][r] = L;
+  }
+  __syncthreads();
   if (threadIdx.x < kD) {
-    const int d = threadIdx.x;
-    const int nparts = kWarps + (owner ? 1 : 0);
+    const int d = 16 * (threadIdx.x & 7) + (threadIdx.x >> 3);  // the dim whose partials sit at offset threadIdx.x
     float* part = nullptr;
     if (nsplit > 1) part = ws_part + ((static_cast<size_t>(b) * num_heads + h0) * nsplit + split) * (kD + 2);
+    const float vd = __half2float(s_v[d]);
 #pragma unroll
     for (int r = 0; r < kMaxG; ++r) {
       if (r < Gc) {
-        float M = -CUDART_INF_F;
-        for (int w = 0; w < nparts; ++w) M = fmaxf(M, s_m[w][r]);
-        float L = 0.f, acc = 0.f;
-        for (int w = 0; w < kWarps; ++w) {
-          const float e = (s_m[w][r] == -CUDART_INF_F) ? 0.f : exp2f(s_m[w][r] - M);
-          L += s_l[w][r] * e;
-          acc += s_o[(w * kMaxG + r) * kD + d] * e;
-        }
-        if (owner) {
-          const float e = exp2f(s_m[kWarps][r] - M);
-          L += e;
-          acc += e * __half2float(s_v[d]);
-        }
+        float acc = s_f[kWarps][r] * vd;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+          acc = fmaf(reinterpret_cast<const float*>(s_ring + w * SL::kWarpBytes)[r * kOStride + threadIdx.x], s_f[w][r], acc);
         if (nsplit == 1) {
-          // reference normalisation: 1 / (sum + 1e-6)   (Template.hpp:1818)
-          out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc * __fdividef(1.f, L + 1.e-6f));
+          out[(static_cast<size_t>(b) * num_heads + h0 + r) * kD + d] = __float2half_rn(acc);
         } else {
           float* pr = part + static_cast<size_t>(r) * nsplit * (kD + 2);
           pr[d] = acc;
-          if (d == 0) {
-            pr[kD] = M;
-            pr[kD + 1] = L;
+          if (threadIdx.x == 0) {
+            pr[kD] = s_m[0][r];
+            pr[kD + 1] = s_l[0][r];
           }
         }
       }
     }
   }
   qs_trace(QS_K_ATTN, 2);
+  if (threadIdx.x == 0) ATTN_PROF(8);
   bool final_written = (nsplit == 1);  // this CTA produced the final fp16 outputs of its head group
   if (nsplit > 1) {
     __threadfence();
@@ -681,6 +713,8 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       }
     }
   }
+  if (threadIdx.x == 0) ATTN_PROF(9);
+#undef ATTN_PROF
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -891,13 +925,11 @@ int decode_attention(const DecodeAttnArgs& a) {
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(a.q),
                       static_cast<const __half*>(a.k), static_cast<const __half*>(a.v), a.q_stride, a.k_stride, a.v_stride, a.kv_pointers, a.lengths,
                       static_cast<__half*>(out), a.num_heads, a.num_kv_heads, a.max_blocks, pg, a.rotary_base, a.rotary_dim, a.timestep, nsplit,
-                      part, cnt, tok_cnt, static_cast<int8_t*>(a.q_out), static_cast<__half*>(a.q_scale), static_cast<__half*>(a.q_sum)), "single_query_attention");
+                      part, cnt, tok_cnt, static_cast<int8_t*>(a.q_out), static_cast<__half*>(a.q_scale), static_cast<__half*>(a.q_sum), static_cast<unsigned long long*>(a.prof)), "single_query_attention");
   };
-  QS_REQUIRE((a.timestep + 63) / 64 + 1 <= kMaxBlocksSmem, "single_query_attention: context of %d tokens exceeds the %d pages staged in shared memory", a.timestep, kMaxBlocksSmem);
   QS_REQUIRE(a.tokens_per_block == kPageTokens, "single_query_attention: tokens_per_block=%d, only 64 is supported (cache_engine block_size)", a.tokens_per_block);
-  constexpr size_t kMerge = sizeof(float) * kWarps * kMaxG * kD;
-  const size_t s4 = StageLayout<4>::kBytes * StageLayout<4>::kStages, s8 = StageLayout<8>::kBytes * StageLayout<8>::kStages;
-  return a.int4_kv ? run(decode_attention_kernel<4>, s4 > kMerge ? s4 : kMerge) : run(decode_attention_kernel<8>, s8 > kMerge ? s8 : kMerge);
+  return a.int4_kv ? run(decode_attention_kernel<4>, static_cast<size_t>(kWarps) * StageLayout<4>::kWarpBytes)
+                   : run(decode_attention_kernel<8>, static_cast<size_t>(kWarps) * StageLayout<8>::kWarpBytes);
 }
 
 int prefill_rope_append(const PrefillAppendArgs& a) {

@@ -118,18 +118,28 @@ __device__ __forceinline__ int2 ld_dsmem_v2(uint32_t addr) {
   return v;
 }
 
+// INT32 -> FP32, round to nearest even, WITHOUT the conversion unit (I2F issues once per 16 cycles per SM sub-partition on the
+// XU pipe, and the epilogue needs one per output):  v = hi * 65536 + lo, both halves are converted exactly by the 1.5 * 2^23
+// magic-number add, and the single rounding of the fused multiply-add equals cvt.rn.f32.s32(v).
+__device__ __forceinline__ float int2float_rn_noxu(int32_t v) {
+  const int32_t hi = v >> 16, lo = v & 0xFFFF;
+  const float fhi = __fsub_rn(__int_as_float(0x4B400000 + hi), 12582912.f);
+  const float flo = __fsub_rn(__int_as_float(0x4B400000 + lo), 12582912.f);
+  return __fmaf_rn(fhi, 65536.f, flo);
+}
+
 template <int MODE>
-__device__ __forceinline__ __half epilogue_one(int32_t acc, float ws, float wsz, float as, float asum) {
+__device__ __forceinline__ float epilogue_one(int32_t acc, float ws, float wsz, float as, float asum) {
   // IEEE fp32, reference source order, no FMA contraction (bit-exact against oracle/w4a8.py)
-  float ps = __int2float_rn(acc);
+  float ps = int2float_rn_noxu(acc);
   if constexpr (MODE == kModeW4Chn) {
     // w4a8_per_chn/gemm_cuda.cu:586  psum * wscale * ascale - w_sz * a_ssum
     float t = __fmul_rn(__fmul_rn(ps, ws), as);
     float u = __fmul_rn(wsz, asum);
-    return __float2half_rn(__fsub_rn(t, u));
+    return __fsub_rn(t, u);
   } else {
     // w4a8_per_group/gemm_cuda.cu:619, w8a8_gemm_cuda.cu:522   psum *= wscale * ascale
-    return __float2half_rn(__fmul_rn(ps, __fmul_rn(ws, as)));
+    return __fmul_rn(ps, __fmul_rn(ws, as));
   }
 }
 
@@ -389,9 +399,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
     const size_t ostep = static_cast<size_t>(tstep) * p.N;
     auto finish = [&](int tok, int2 acc, __half* dst) {
       const float as = s_asc[tok], asum = s_asum[tok];
-      const __half o0 = epilogue_one<MODE>(acc.x, ws0, wz0, as, asum);
-      const __half o1 = epilogue_one<MODE>(acc.y, ws1, wz1, as, asum);
-      *reinterpret_cast<__half2*>(dst) = __halves2half2(o0, o1);
+      const float o0 = epilogue_one<MODE>(acc.x, ws0, wz0, as, asum);
+      const float o1 = epilogue_one<MODE>(acc.y, ws1, wz1, as, asum);
+      *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(o0, o1);  // one packed conversion, each half rounded to nearest even
       if constexpr (ACC) *reinterpret_cast<int2*>(p.acc_out + (dst - p.out)) = acc;
     };
     // tokens per thread: NT / (4 S); every round has 16 (distributed-)shared-memory loads in flight per thread

@@ -65,6 +65,7 @@ struct DecodeAttnArgs {
   void* q_out = nullptr;                   // fused-quant extension: int8 [B, Hq*D] (then `out` is not written)
   void* q_scale = nullptr;                 //   fp16 [B]
   void* q_sum = nullptr;                   //   fp16 [B] or null
+  void* prof = nullptr;                    // optional: 16 globaltimer stamps per CTA (tools/attn_timeline.py)
   int batch = 0, num_heads = 0, num_kv_heads = 0, head_dim = 0, max_blocks = 0;
   int tokens_per_block = 64, size_per_token = 0, timestep = 0, memory_max_len = 0;
   int rotary_dim = 0;
