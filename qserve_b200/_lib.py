@@ -22,6 +22,7 @@ SIGNATURES = {
     "qs_w8a8_gemm": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "qs_gemm_workspace_bytes": (c_size_t, []),
     "qs_gemm_force_split": (c_int, [_I]),
+    "qs_gemm_force_tile_tokens": (c_int, [_I]),
     "qs_gemm_set_profile_buffer": (c_int, [_P]),
     "qs_set_trace_buffer": (c_int, [_P, ctypes.c_uint]),
     "qs_single_query_attention": (c_int, [_P, _P, _P, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P, _Z, _P]),

@@ -11,6 +11,7 @@ namespace qs {
 static thread_local char g_err[1024] = "";
 static int g_pdl = 1;
 static int g_force_split = 0;
+static int g_force_nt = 0;
 static void* g_gemm_prof = nullptr;
 
 int set_error(int code, const char* fmt, ...) {
@@ -44,6 +45,12 @@ int qs_set_pdl(int enabled) {
   g_pdl = enabled ? 1 : 0;
   return old;
 }
+int qs_gemm_force_tile_tokens(int nt) {
+  const int old = g_force_nt;
+  g_force_nt = nt;
+  return old;
+}
+
 int qs_gemm_force_split(int split) {
   const int old = g_force_split;
   g_force_split = split;
@@ -68,7 +75,7 @@ int qs_w4a8_gemm_per_chn(const int8_t* in_feats, const int8_t* kernel, const voi
   GemmArgs a;
   a.act = in_feats; a.weight = kernel; a.wscales = wscales; a.ascales = ascales; a.w_szs = w_szs; a.a_ssums = a_ssums;
   a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
-  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.prof = g_gemm_prof; a.stream = stream;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.force_nt = g_force_nt; a.prof = g_gemm_prof; a.stream = stream;
   return gemm_w4a8_per_chn(a);
 }
 
@@ -80,7 +87,7 @@ int qs_w4a8_gemm_per_group(const int8_t* in_feats, const int8_t* kernel, const i
   GemmArgs a;
   a.act = in_feats; a.weight = kernel; a.s2_zeros = zeros; a.s2_scales = scales_i8; a.wscales = wscales; a.ascales = ascales;
   a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
-  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.prof = g_gemm_prof; a.stream = stream;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.force_nt = g_force_nt; a.prof = g_gemm_prof; a.stream = stream;
   return gemm_w4a8_per_group(a);
 }
 
@@ -90,7 +97,7 @@ int qs_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void* wscal
   GemmArgs a;
   a.act = in_feats; a.weight = kernel; a.wscales = wscales; a.ascales = ascales;
   a.out = out_feats; a.acc_out = acc_out; a.M = M; a.N = N; a.K = K;
-  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.prof = g_gemm_prof; a.stream = stream;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.force_split = g_force_split; a.force_nt = g_force_nt; a.prof = g_gemm_prof; a.stream = stream;
   return gemm_w8a8(a);
 }
 

@@ -543,6 +543,8 @@ int choose_split(int tiles, int kb_per_tile, int forced) {
     const int sms = num_sms();
     // smallest power of two that brings the CTA count to >= ~2/3 of the SMs; every CTA keeps >= 2 k-blocks
     while (s < 8 && tiles * s < (2 * sms) / 3 && kb_per_tile / (2 * s) >= 1) s *= 2;
+    // long-K layers (down_proj): one more doubling while every CTA still streams >= 6 stages -- more bytes in flight per SM
+    if (s == 4 && tiles * s < sms && kb_per_tile / 8 >= 6) s = 8;
   }
   if (s > 8) s = 8;
   while (s > 1 && kb_per_tile < s) s /= 2;
@@ -608,9 +610,14 @@ int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.force_split == 0 || a.force_split == 1 || a.force_split == 2 || a.force_split == 4 || a.force_split == 8, "gemm: split must be 1, 2, 4 or 8");
   // weight-ring depths (256-K stages) chosen so that NT <= 128 fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns)
   constexpr bool w8 = (MODE == kModeW8), grp = (MODE == kModeW4Grp);
-  if (a.M <= 32) return launch_gemm<MODE, 32, (w8 ? 2 : grp ? 4 : 5), 4>(a);
-  if (a.M <= 64) return launch_gemm<MODE, 64, (w8 ? 2 : grp ? 3 : 4), 3>(a);
-  if (a.M <= 128) return launch_gemm<MODE, 128, (w8 ? 4 : 2), 2>(a);
+  QS_REQUIRE(a.force_nt == 0 || a.force_nt == 32 || a.force_nt == 64 || a.force_nt == 128 || a.force_nt == 256, "gemm: tile tokens must be 32, 64, 128 or 256");
+  int nt = a.force_nt;
+  if (nt == 0) {
+    nt = a.M <= 32 ? 32 : a.M <= 64 ? 64 : a.M <= 128 ? 128 : 256;
+  }
+  if (nt == 32) return launch_gemm<MODE, 32, (w8 ? 2 : grp ? 4 : 5), 4>(a);
+  if (nt == 64) return launch_gemm<MODE, 64, (w8 ? 2 : grp ? 3 : 4), 3>(a);
+  if (nt == 128) return launch_gemm<MODE, 128, (w8 ? 4 : 2), 2>(a);
   return launch_gemm<MODE, 256, (w8 ? 2 : 5), 2>(a);
 }
 

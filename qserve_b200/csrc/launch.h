@@ -22,6 +22,7 @@ struct GemmArgs {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int force_split = 0;          // tests: force the cluster split-K factor (1, 2, 4, 8); 0 = automatic
+  int force_nt = 0;             // tests / tuning: force the tokens-per-tile (32, 64, 128, 256); 0 = automatic
   void* prof = nullptr;         // optional device buffer: 16 x uint64 globaltimer stamps per CTA
   void* stream = nullptr;
 };
