@@ -92,6 +92,16 @@ class ClockSampler:
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def ncu_traffic(kernel: str):
+    """dram bytes per launch of `kernel` from the newest committed ncu capture summary (profiles/rNN_ncu_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None
+    d = json.load(open(files[-1])).get(kernel)
+    return None if not d else int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -311,7 +321,8 @@ def main():
         "gpu_launches": run.launches_per_step * args.steps,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": f"gemm_kernel W4A8 gate_up_proj M={dom['M']} N={dom['N']} K={dom['K']} (tcgen05, dominant: 54% of the GEMM bytes)",
-                     "achieved": dom["GBps"], "peak": hbm_gbs, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src, "traffic": None,
+                     "achieved": dom["GBps"], "peak": hbm_gbs, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src, "traffic": ncu_traffic("gemm_gate_up"),
+                     "traffic_unit": "dram bytes per launch (ncu --set full)", "algorithmic_bytes": dom["bytes"],
                      "us_per_launch": dom["us"]},
         "kernels": kern,
         "step_hbm_frac": (step_bytes / (ms_dev / args.steps * 1e-3)) / 1e9 / hbm_gbs,

@@ -39,9 +39,6 @@ __device__ __forceinline__ uint32_t lop3_and_or(uint32_t x, uint32_t mask, uint3
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(x), "r"(mask), "r"(orv));  // (x & mask) | orv
   return d;
 }
-__device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
-  return static_cast<uint32_t>(__half_as_ushort(lo)) | (static_cast<uint32_t>(__half_as_ushort(hi)) << 16);
-}
 __device__ __forceinline__ uint32_t pack_f2h2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
