@@ -201,6 +201,24 @@ def kernel_rooflines(run, reps, hbm_gbs):
     t = time_kernel(attn, reps, stream)
     b = run.kv_bytes_per_step() // run.L
     out["attention"] = {"B": M, "Hq": run.Hq, "Hkv": run.Hkv, "ctx": run.ctx, "us": t * 1e6, "bytes": b, "GBps": b / t / 1e9, "frac": b / t / 1e9 / hbm_gbs}
+
+    # prefill-sized GEMM (tensor-pipe bound, SURVEY.md 8d "GEMM INT8-TC util"): 4096 tokens through gate_up_proj
+    Mp = 4096
+    lin = run.layers[0]["gate_up"]
+    xq = torch.randint(-127, 128, (Mp, lin.K), dtype=torch.int8, device=run.q_hidden.device)
+    sc = torch.full((Mp,), 0.01, dtype=torch.half, device=xq.device)
+    sm = torch.zeros((Mp,), dtype=torch.half, device=xq.device)
+    big = torch.empty((Mp, lin.N), dtype=torch.half, device=xq.device)
+
+    def prefill():
+        for ly in run.layers[:4]:
+            ly["gate_up"](xq, sc, sm, big)
+        return 4
+    t = time_kernel(prefill, max(2, reps // 8), stream)
+    ops = 2.0 * Mp * lin.N * lin.K
+    out["gemm_prefill_gate_up"] = {"M": Mp, "N": lin.N, "K": lin.K, "us": t * 1e6, "int8_TOPS": ops / t / 1e12,
+                                   "frac_of_nominal_int8_dense": ops / t / 1e12 / 4500.0, "bound": "tensor (INT8 dense nominal 4.5 POP/s)"}
+    del big
     return out
 
 

@@ -141,6 +141,41 @@ def test_llama3_8b_layer_shapes_decode_b64(dev):
         assert np.array_equal(bits16(np_of(out)), bits16(out_o)), (K, N)
 
 
+CONFIG_SHAPES = [  # BASELINE.json configs 3-5: (mode, M, N, K)
+    ("grp", 64, 6144, 4096), ("grp", 64, 4096, 14336),                                  # 3: Llama-3-8B g128, decode batch 64
+    ("w8", 128, 6144, 4096), ("w8", 128, 28672, 4096), ("w8", 128, 4096, 14336),        # 4: Mistral-7B W8A8, decode batch 128
+    ("chn", 64, 6144, 8192), ("chn", 64, 8192, 2048), ("chn", 64, 12288, 8192), ("chn", 64, 8192, 6144),  # 5: Qwen1.5-72B, TP=4 shards
+]
+
+
+@pytest.mark.parametrize("mode,M,N,K", CONFIG_SHAPES)
+def test_baseline_config_shapes_bit_exact(dev, mode, M, N, K):
+    """The GEMM shapes of BASELINE configs 3, 4 and 5 (per-rank shards at TP=4): INT32 and FP16 bit-exact at full size."""
+    rng = np.random.default_rng(N + K + M)
+    aq, sa, asum = _acts(rng, M, K)
+    out = torch.empty((M, N), dtype=torch.half, device=dev)
+    acc = torch.zeros((M, N), dtype=torch.int32, device=dev)
+    if mode == "chn":
+        import qserve_backend.qgemm_w4a8_per_chn as op
+        q, qw, s1, s1z = w4a8.synth_per_channel(rng, N, K)
+        out_o, acc_o = w4a8.gemm_w4a8_per_chn(aq, qw, s1, sa, s1z, asum, return_acc=True)
+        op.gemm_forward_cuda(*[to_dev(a, dev) for a in (aq, qw, s1, sa, s1z, asum)], out, _acc_out=acc)
+    elif mode == "grp":
+        import qserve_backend.qgemm_w4a8_per_group as op
+        q, qw, s1, s2s, s2z = w4a8.synth_per_group(rng, N, K)
+        out_o, acc_o = w4a8.gemm_w4a8_per_group(aq, qw, s2z, s2s, s1, sa, return_acc=True)
+        op.gemm_forward_cuda(*[to_dev(a, dev) for a in (aq, qw, s2z, s2s, s1, sa)], out, _acc_out=acc)
+    else:
+        import qserve_backend.qgemm_w8a8 as op
+        w = rng.integers(-128, 128, size=(N, K), dtype=np.int8)
+        sw = rng.uniform(0.001, 0.01, size=N).astype(np.float16)
+        out_o, acc_o = w4a8.gemm_w8a8(aq, w, sw, sa, return_acc=True)
+        op.w8a8_gemm_forward_cuda(*[to_dev(a, dev) for a in (aq, w, sw, sa)], out, _acc_out=acc)
+    torch.cuda.synchronize()
+    assert np.array_equal(np_of(acc), acc_o)
+    assert np.array_equal(bits16(np_of(out)), bits16(out_o))
+
+
 def test_linearity_property_full_size(dev):
     """Size-independent property at prefill size (M=2048): acc(a1 + a2) == acc(a1) + acc(a2) for the INT32 accumulators."""
     import qserve_backend.qgemm_w4a8_per_chn as op
