@@ -315,17 +315,27 @@ def main():
             cpu = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": threads, "kind": "port",
                    "sample": f"1 of {cfg.layers} decoder layers (4 W4A8 GEMMs M={args.batch} + KV4 attention B={args.batch} ctx={args.ctx}) + lm_head on torch-CPU "
                              f"dequant-then-matmul, extrapolated x{cfg.layers}; {r['layer_s']:.2f} s/layer (dequant {r['dequant_s']:.2f}, matmul {r['matmul_s']:.2f}, attention {r['attention_s']:.2f})"}
+    def finish():
+        # tear down in a fixed order: drop the CUDA graph (it holds NCCL kernels under TP) before the communicator, and do not
+        # let a slow communicator teardown keep the launcher alive after the result line is out
+        sys.stdout.flush()
+        if world > 1:
+            run.graph = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish()
         return
 
     dom = kern["gemm_gate_up"]
     step_bytes = run.weight_bytes_per_step() + run.kv_bytes_per_step() + 2 * cfg.vocab * cfg.hidden
     line = {
-        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC if (args.model, args.precision, args.batch) == ("llama-3-8b", "w4a8kv4", 64) else f"tokens/s {cfg.name} {args.precision} decode b{args.batch}",
+        "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if tp == 1 else "strong", "vs_baseline": None,
         "dtype": "s8" if args.precision.startswith("w4a8") or args.precision.startswith("w8a8") else "f16", "data": "synthetic",
         "config": {"workload": f"{cfg.name} {args.precision} decode batch={args.batch} ctx={args.ctx} ({'CUDA-graph replay' if not args.no_graph else 'eager'}; "
@@ -339,7 +349,8 @@ def main():
         "gpu_launches": run.launches_per_step * args.steps,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": f"gemm_kernel W4A8 gate_up_proj M={dom['M']} N={dom['N']} K={dom['K']} (tcgen05, dominant: 54% of the GEMM bytes)",
-                     "achieved": dom["GBps"], "peak": hbm_gbs, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src, "traffic": ncu_traffic("gemm_gate_up"),
+                     "achieved": dom["GBps"], "peak": hbm_gbs, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src,
+                     "traffic": ncu_traffic("gemm_gate_up") if (dom["M"], dom["N"], dom["K"]) == (64, 28672, 4096) else None,
                      "traffic_unit": "dram bytes per launch (ncu --set full)", "algorithmic_bytes": dom["bytes"],
                      "us_per_launch": dom["us"]},
         "kernels": kern,
@@ -348,8 +359,7 @@ def main():
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
