@@ -164,6 +164,9 @@ QS_API int qs_single_query_attention_quant(const void* q, const void* k, const v
                                            int rotary_embedding_dim, float rotary_base, int int4_kv_cache, int kv_cache_with_zeros, void* workspace,
                                            size_t workspace_bytes, void* stream);
 /* silu_and_mul(input [tokens, 2d]) followed by invoke_quant[_fuse_sum](out, act, input_sum | NULL, scale)                 */
+/* greedy sampling helper for the decode runner: out[r] = index of the first maximum of logits[r, :] (fp16, NaN = maximum), as
+ * torch.argmax(logits, -1) does in the reference's sampler */
+QS_API int qs_argmax_rows(int64_t* out, const void* logits, int rows, int vocab, void* stream);
 QS_API int qs_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int tokens, int d, void* stream);
 
 #ifdef __cplusplus

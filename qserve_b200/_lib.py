@@ -21,6 +21,7 @@ SIGNATURES = {
     "qs_w4a8_gemm_per_group": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "qs_w8a8_gemm": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "qs_gemm_workspace_bytes": (c_size_t, []),
+    "qs_argmax_rows": (c_int, [_P, _P, _I, _I, _P]),
     "qs_gemm_force_split": (c_int, [_I]),
     "qs_gemm_force_tile_tokens": (c_int, [_I]),
     "qs_gemm_set_profile_buffer": (c_int, [_P]),

@@ -402,3 +402,15 @@ def single_query_attention_quant(q, k, v, kv_pointers, length_per_sample, memory
                                               kv_pointers.size(-1), int(memory_max_seqlen), int(tokens_per_block), int(size_per_token), int(timestep),
                                               int(rotary_embedding_dim), float(rotary_base), int(bool(int4_kv_cache)), int(bool(kv_cache_with_zeros)),
                                               ws.data_ptr(), ws.numel(), _stream(q)))
+
+
+def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch.argmax(logits, dim=-1) for fp16 logits [rows, vocab] in one launch (greedy sampling of the decode runner)."""
+    _cuda(logits, "logits")
+    _require(logits.dtype == _HALF and logits.dim() == 2 and logits.is_contiguous(), "logits must be contiguous float16 [rows, vocab]")
+    if out is None:
+        out = torch.empty(logits.size(0), dtype=torch.int64, device=logits.device)
+    if logits.size(0) == 0:
+        return out
+    check(lib.qs_argmax_rows(out.data_ptr(), logits.data_ptr(), logits.size(0), logits.size(1), _stream(logits)))
+    return out

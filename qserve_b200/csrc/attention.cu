@@ -162,10 +162,10 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
   if (threadIdx.x == 0) ATTN_PROF(0);
   qs_trace(QS_K_ATTN, 0);
   if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
-  pdl_wait();
-  qs_trace(QS_K_ATTN, 1);
-  if (threadIdx.x == 0) ATTN_PROF(1);
 
+  // The sequence lengths and the page-pointer table are prepared by the host side before the step (model_runner.py:506-530):
+  // they are read BEFORE the dependency wait, so that the chain length -> page pointers -> first bulk copy (two dependent
+  // global round trips) overlaps the tail of the preceding qkv GEMM.  Page CONTENTS and q/k/v are only touched after the wait.
   const int tlen = (lengths ? lengths[b] : timestep) - 1;  // tokens already in the cache (Template.hpp:901)
   const long long* kptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 0) * max_blocks;
   const long long* vptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 1) * max_blocks;
@@ -206,6 +206,9 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
     }
   };
   load_ptr_batch(0);
+  pdl_wait();
+  qs_trace(QS_K_ATTN, 1);
+  if (threadIdx.x == 0) ATTN_PROF(1);
   for (int j = 0; j < R && j < n_my; ++j) issue(j, j);  // the cache stream starts before the new-token work below
   if (threadIdx.x == 0) ATTN_PROF(3);
   {

@@ -208,6 +208,12 @@ int qs_invoke_dequant(void* out, const int32_t* input, float scale, int tokens, 
   return dequant(out, input, scale, tokens, hidden, input_stride, out_stride, stream);
 }
 
+int qs_argmax_rows(int64_t* out, const void* logits, int rows, int vocab, void* stream) {
+  QS_REQUIRE(out && logits, "argmax_rows: null tensor");
+  QS_REQUIRE(aligned16(logits) && (static_cast<size_t>(vocab) * 2) % 16 == 0, "argmax_rows: rows must be 16-byte aligned");
+  return argmax_rows(out, logits, rows, vocab, stream);
+}
+
 int qs_silu_and_mul_quant(int8_t* out, const void* input, void* input_sum, void* scale, int tokens, int d, void* stream) {
   QS_REQUIRE(out && input && scale, "silu_and_mul_quant: null tensor");
   QS_REQUIRE(aligned16(out) && aligned16(input), "silu_and_mul_quant: tensors must be 16-byte aligned");

@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_quant_kernel(int8_t* __res
 // ------------------------------------------------------------------------------------------------
 constexpr int kFusedThreads = kThreads;  // same thread count and loop order as the unfused kernels -> bit-identical sums
 
+constexpr int kGammaPre = 4;  // gamma chunks (8 halves each) a thread keeps in registers: covers H <= 8192 at 256 threads
 __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8_t* __restrict__ out, __half* __restrict__ hidden_out,
                                                                            const __half* __restrict__ x, const __half* __restrict__ delta,
                                                                            const __half* __restrict__ gamma, __half* __restrict__ input_sum,
@@ -194,6 +195,13 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
   const int row = blockIdx.x;
   qs_trace(QS_K_ADDNORM, 0);
   if (threadIdx.x == 0) pdl_launch_dependents();  // dependents may become resident (and prefetch static data) right away
+  // gamma is a static weight: fetch this thread's chunks before waiting for the producer of x / delta
+  uint4 gpre[kGammaPre];
+#pragma unroll
+  for (int e = 0; e < kGammaPre; ++e) {
+    const int i = threadIdx.x + e * blockDim.x;
+    gpre[e] = (i < H / 8) ? __ldg(reinterpret_cast<const uint4*>(gamma) + i) : make_uint4(0u, 0u, 0u, 0u);
+  }
   pdl_wait();
   qs_trace(QS_K_ADDNORM, 1);
   {
@@ -241,9 +249,8 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
   const float var = block_reduce(vs, red, OpSum(), 0.f);
   const float rstd = __frsqrt_rn(__fadd_rn(__fdiv_rn(var, static_cast<float>(H)), eps));
   float amax = __half2float(__float2half_rn(1e-6f));
-  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+  auto norm_chunk = [&](int i, const uint4& g) {
     const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
-    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
     const __half* h = reinterpret_cast<const __half*>(&v);
     const __half* gh = reinterpret_cast<const __half*>(&g);
     uint4 yv;
@@ -255,7 +262,13 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
       amax = fmaxf(amax, fabsf(__half2float(yh[j])));
     }
     if (input_sum) reinterpret_cast<uint4*>(sy)[i] = yv;
+  };
+#pragma unroll
+  for (int e = 0; e < kGammaPre; ++e) {
+    const int i = threadIdx.x + e * blockDim.x;
+    if (i < H / 8) norm_chunk(i, gpre[e]);
   }
+  for (int i = threadIdx.x + kGammaPre * blockDim.x; i < H / 8; i += blockDim.x) norm_chunk(i, __ldg(reinterpret_cast<const uint4*>(gamma) + i));
   amax = block_reduce(amax, red, OpMax(), 0.f);
   if (input_sum) {
     long long part = 0;
@@ -269,16 +282,21 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
   }
   if (threadIdx.x == 0) scaling[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
   const float qs_ = __fdiv_rn(127.f, amax);
-  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+  auto quant_chunk = [&](int i, const uint4& g) {
     const uint4 v = reinterpret_cast<const uint4*>(sx)[i];
-    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma) + i);
     const __half* h = reinterpret_cast<const __half*>(&v);
     const __half* gh = reinterpret_cast<const __half*>(&g);
     float y[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = __fmul_rn(__fmul_rn(__fsub_rn(__half2float(h[j]), mean), rstd), __half2float(gh[j]));
     store_q8(out + static_cast<size_t>(row) * H, i, y, qs_);
+  };
+#pragma unroll
+  for (int e = 0; e < kGammaPre; ++e) {
+    const int i = threadIdx.x + e * blockDim.x;
+    if (i < H / 8) quant_chunk(i, gpre[e]);
   }
+  for (int i = threadIdx.x + kGammaPre * blockDim.x; i < H / 8; i += blockDim.x) quant_chunk(i, __ldg(reinterpret_cast<const uint4*>(gamma) + i));
 }
 
 __device__ __forceinline__ __half silu_h_fused(__half x) {
@@ -585,6 +603,68 @@ __global__ void __launch_bounds__(kThreads) dequant_silu_and_mul_quant_kernel(in
     out[static_cast<size_t>(row) * d + i] = cvt_s8(__fmul_rn(qs_, tmp[static_cast<size_t>(row) * d + i]));
 }
 
+// ---------------------------------------------------------------------------------------------
+// greedy sampling: argmax over the vocabulary of fp16 logits [rows, V] (the reference samples with torch.argmax).
+// A cluster of 8 CTAs per row: each scans V/8 logits with 128-bit loads, the (value, index) pairs are combined through
+// distributed shared memory.  First maximal index wins, NaN counts as the maximum (torch semantics).
+// ---------------------------------------------------------------------------------------------
+constexpr int kArgmaxCluster = 8;
+__device__ __forceinline__ bool argmax_better(float v, int i, float bv, int bi) {
+  const bool vn = (v != v), bn = (bv != bv);
+  if (vn != bn) return vn;
+  if (vn) return i < bi;
+  return v > bv || (v == bv && i < bi);
+}
+__global__ void __launch_bounds__(kThreads) argmax_rows_kernel(long long* __restrict__ out, const __half* __restrict__ logits, int V) {
+  __shared__ float s_v[kThreads / 32];
+  __shared__ int s_i[kThreads / 32];
+  __shared__ __align__(8) int2 s_part;  // (float bits, index) of this CTA
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x / kArgmaxCluster, part = blockIdx.x % kArgmaxCluster;
+  const __half* src = logits + static_cast<size_t>(row) * V;
+  const int nvec = V / 8;  // V % 8 == 0 (checked on the host)
+  const int v0 = static_cast<int>((static_cast<long long>(nvec) * part) / kArgmaxCluster);
+  const int v1 = static_cast<int>((static_cast<long long>(nvec) * (part + 1)) / kArgmaxCluster);
+  float best = __int_as_float(0xff800000);  // -inf
+  int bi = 0x7fffffff;
+  for (int i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f = __half2float(h[j]);
+      if (argmax_better(f, i * 8 + j, best, bi)) { best = f; bi = i * 8 + j; }
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, m);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+    if (argmax_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w)
+      if (argmax_better(s_v[w], s_i[w], best, bi)) { best = s_v[w]; bi = s_i[w]; }
+    s_part = make_int2(__float_as_int(best), bi);
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (part == 0 && threadIdx.x == 0) {
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part));
+    for (int r = 1; r < kArgmaxCluster; ++r) {
+      uint32_t peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(base), "r"(r));
+      int pv, pi;
+      asm volatile("ld.shared::cluster.v2.s32 {%0, %1}, [%2];" : "=r"(pv), "=r"(pi) : "r"(peer) : "memory");
+      if (argmax_better(__int_as_float(pv), pi, best, bi)) { best = __int_as_float(pv); bi = pi; }
+    }
+    out[row] = bi;
+  }
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");  // peers' smem stays valid
+}
+
 template <typename Kern, typename... Args>
 int launch(Kern kern, dim3 grid, dim3 block, size_t smem, void* stream, const char* what, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -738,6 +818,26 @@ int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void
   return launch(add_layernorm_quant_kernel, dim3(tokens), dim3(kFusedThreads), smem, stream, "add_rms_norm_general", static_cast<int8_t*>(out_q),
                 static_cast<__half*>(hidden_out), static_cast<const __half*>(x), static_cast<const __half*>(delta),
                 static_cast<const __half*>(gamma), static_cast<__half*>(input_sum), static_cast<__half*>(scaling), eps, hidden, ref_block);
+}
+
+int argmax_rows(void* out, const void* logits, int rows, int vocab, void* stream) {
+  if (rows == 0) return QS_OK;
+  QS_REQUIRE(vocab > 0 && vocab % 8 == 0, "argmax_rows: vocab=%d must be a positive multiple of 8", vocab);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(rows * kArgmaxCluster);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = kArgmaxCluster;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return check_cuda(cudaLaunchKernelEx(&cfg, argmax_rows_kernel, static_cast<long long*>(out), static_cast<const __half*>(logits), vocab), "argmax_rows");
 }
 
 }  // namespace qs

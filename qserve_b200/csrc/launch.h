@@ -42,6 +42,7 @@ int layernorm_general_quant(void* out_q, const void* in, const void* gamma, void
 int quant_per_token(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int hidden, void* stream);
 int quant_scalar(void* out_q, const void* in, float scale, int tokens, int hidden, void* stream);
 int silu_and_mul(void* out, const void* in, int tokens, int d, void* stream);
+int argmax_rows(void* out_i64, const void* logits_f16, int rows, int vocab, void* stream);
 int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int d, void* stream);
 int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void* delta, const void* gamma, void* input_sum, void* scaling, float eps,
                         int tokens, int hidden, void* stream);

@@ -106,3 +106,20 @@ def test_attention_quant_equals_attention_then_quant(dev, bits, B, Hq, Hkv, lens
     (q1, s1, m1, k1, v1), (q2, s2, m2, k2, v2) = res
     assert np.array_equal(k1, k2) and np.array_equal(v1, v2)
     assert torch.equal(q1, q2) and torch.equal(s1, s2) and torch.equal(m1, m2)
+
+
+@pytest.mark.parametrize("rows,vocab", [(64, 128256), (3, 32000), (1, 1024), (5, 152064)])
+def test_argmax_rows_matches_torch(dev, rows, vocab):
+    """argmax_rows == torch.argmax(dim=-1), including ties (first index wins) and NaN (counts as the maximum)."""
+    from qserve_b200 import backend as ext
+    g = torch.Generator(device="cpu").manual_seed(rows + vocab)
+    x = torch.randn((rows, vocab), generator=g).half()
+    x[0, 7] = x[0].max() ; x[0, vocab - 5] = x[0, 7]          # a tie: the first index must win
+    if rows > 1:
+        x[1, 123] = float("nan")
+    xd = x.to(dev)
+    got = ext.argmax_rows(xd)
+    torch.cuda.synchronize()
+    want = torch.argmax(xd, dim=-1)
+    assert torch.equal(got, want)
+    assert int(got[0]) <= 7
