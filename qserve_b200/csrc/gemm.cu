@@ -38,7 +38,8 @@ constexpr int kBM = 128;  // output channels per tile (UMMA M)
 constexpr int kBK = 128;  // K sub-block (= one g128 group, one 128-byte swizzled activation row)
 constexpr int kSub = 2;    // sub-blocks per pipeline stage: per-stage barrier latencies are amortised over 256 K
 constexpr int kNumThreads = 256;
-// warp roles: 0 weight producer | 1 TMEM owner + MMA issuer | 2..5 unpack + TMEM epilogue | 6 activation producer | 7 spare.
+// warp roles: 0 weight producer | 1 TMEM owner + MMA issuer (even stages) | 2..5 unpack + TMEM epilogue | 6 activation producer |
+// 7 MMA issuer (odd stages).
 // All eight warps take part in the final reduce / scale / store phase.
 
 enum { kModeW4Chn = 0, kModeW4Grp = 1, kModeW8 = 2 };
@@ -85,7 +86,7 @@ struct Cfg {
   static constexpr int kRedBytes = NT * kBM * 4;  // INT32 partial tile [NT][128], aliases the pipeline buffers
   static constexpr int kOffRow = (kPipeBytes > kRedBytes ? kPipeBytes : kRedBytes);  // float ascales[NT], asums[NT]
   static constexpr int kOffBar = kOffRow + 2 * NT * 4;
-  static constexpr int kNumBars = 2 * WS + 2 * kActStages + 2 * (kTA > 0 ? kTA : 1) + 1;
+  static constexpr int kNumBars = 2 * WS + 2 * kActStages + 2 * (kTA > 0 ? kTA : 1) + 2;
   static constexpr int kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr
   static constexpr int kSmemBytes = kOffMisc + 16;
   // two co-resident CTAs per SM when both the TMEM columns (<= 256 each) and the shared memory (<= 113 KB each) allow it
@@ -166,6 +167,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   uint64_t* bar_afull = bar_xempty + kActStages;                           // unpack warps -> MMA (TMEM A stage written)
   uint64_t* bar_aempty = bar_afull + TA;                                   // MMA commit -> unpack warps
   uint64_t* bar_dfull = bar_aempty + TA;
+  uint64_t* bar_zero = bar_dfull + 1;                                        // accumulator zero-filled (4 epilogue warps)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kOffMisc);
 
   const int warp = threadIdx.x >> 5;
@@ -202,7 +204,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       mbar_init(&bar_afull[i], 4);
       mbar_init(&bar_aempty[i], 1);
     }
-    mbar_init(bar_dfull, 1);
+    mbar_init(bar_dfull, 2);  // two MMA issuers
+    mbar_init(bar_zero, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::kTmemCols>(s_tmem);
@@ -258,13 +261,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
         if (++s == kActStages) { s = 0; if (it >= kActStages) ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp == 1 || warp == 7) {
+    // ===================================== two MMA issuers: warp 1 takes the even stages, warp 7 the odd ones =====================
+    // One issuer spends ~1060 cycles per stage: two mbarrier waits (~240 cycles each even on a completed phase), 8 MMAs
+    // (~48 cycles of tensor pipe each) and two commits -- the tensor pipe idles half of the time.  Interleaving two issuers hides
+    // one's waits behind the other's MMAs.  The accumulator is zero-filled up front, so every MMA accumulates and the (integer)
+    // result does not depend on the order in which the two streams reach the tensor pipe.
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_i8(kBM, NT, 1u, 1u);
-      int sw = 0, sx = 0;
-      uint32_t phw = 0, phx = 0;
-      for (int it = 0; it < n_kb; ++it) {
+      constexpr int RW = (MODE == kModeW8) ? WS : TA;
+      const int first = (warp == 1) ? 0 : 1;
+      int sw = first % RW, sx = first % kActStages;
+      uint32_t phw = (first / RW) & 1, phx = (first / kActStages) & 1;
+      mbar_wait(bar_zero, 0);
+      tc_fence_after();
+      for (int it = first; it < n_kb; it += 2) {
         // W4: the unpack warps observed wfull before arriving on afull, so afull alone orders the weight data
         if constexpr (MODE == kModeW8) mbar_wait(&bar_wfull[sw], phw); else mbar_wait(&bar_afull[sw], phw);
         mbar_wait(&bar_xfull[sx], phx);
@@ -275,28 +286,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
           const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + sx * C::kActBytes + u * C::kActSub));
 #pragma unroll
           for (int t = 0; t < kBK / 32; ++t) {
-            const uint32_t acc = (it > 0 || u > 0 || t > 0) ? 1u : 0u;
             if constexpr (MODE == kModeW8) {
               const uint64_t adesc = umma_desc_sw128(smem_u32(s_w + sw * C::kWBytes + u * C::kWSub));
-              umma_i8_ss(tmem_base, adesc + t * 2, bdesc + t * 2, idesc, acc);
+              umma_i8_ss(tmem_base, adesc + t * 2, bdesc + t * 2, idesc, 1u);
             } else {
-              umma_i8_ts(tmem_base, tmem_base + NT + sw * C::kAStageCols + u * (kBK / 4) + t * 8, bdesc + t * 2, idesc, acc);
+              umma_i8_ts(tmem_base, tmem_base + NT + sw * C::kAStageCols + u * (kBK / 4) + t * 8, bdesc + t * 2, idesc, 1u);
             }
           }
         }
         if constexpr (MODE == kModeW8) umma_commit(&bar_wempty[sw]); else umma_commit(&bar_aempty[sw]);
         umma_commit(&bar_xempty[sx]);
-        constexpr int RW = (MODE == kModeW8) ? WS : TA;
-        if (++sw == RW) { sw = 0; phw ^= 1; }
-        if (++sx == kActStages) { sx = 0; phx ^= 1; }
+        sw += 2; if (sw >= RW) { sw -= RW; phw ^= 1; }
+        sx += 2; if (sx >= kActStages) { sx -= kActStages; phx ^= 1; }
       }
-      umma_commit(bar_dfull);
-      QS_PROF(6);
+      if (n_kb > first) umma_commit(bar_dfull); else mbar_arrive(bar_dfull);
+      if (first == 0) QS_PROF(6);
     }
   } else if (warp >= 2 && warp <= 5) {
     // ===================================== unpack + TMEM epilogue warps =====================================
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int epi_tid = quad * 32 + lane; // 0..127 == channel row inside the tile
+    {
+      // zero-fill this quadrant of the accumulator (all MMAs accumulate: see the issuers)
+      const uint32_t tz = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < NT; c += 8) {
+        tmem_st_16x128b_x2(tz + c, 0u, 0u, 0u, 0u);
+        tmem_st_16x128b_x2(tz + c + (16u << 16), 0u, 0u, 0u, 0u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_zero);
+    }
     if constexpr (MODE != kModeW8) {
       int s = 0, ta = 0;
       uint32_t ph = 0, pha = 0;  // pha: parity of the (it / TA - 1)-th completion of aempty[ta]
@@ -374,7 +396,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
     }
     if (epi_tid == 0) QS_PROF(9);
   } else {
-    pdl_wait();  // warp 7 (and the idle lanes' warps reach the barrier below directly): it stores to `out` in the final phase
+    pdl_wait();
   }
 
   // ---------------- cross-CTA (cluster) reduction of the INT32 partial tiles through distributed shared memory ----------------
