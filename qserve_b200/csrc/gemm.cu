@@ -528,7 +528,7 @@ struct WideCfg {
   static constexpr int kRedBytes = NT * 2 * kBM * 4;     // INT32 tile [NT][256]
   static constexpr int kOffRow = (kPipeBytes > kRedBytes ? kPipeBytes : kRedBytes);
   static constexpr int kOffBar = kOffRow + 2 * NT * 4;
-  static constexpr int kNumBars = 2 * WS + 2 * AS + 2 * kTA + 1;
+  static constexpr int kNumBars = 2 * WS + 2 * AS + 2 * kTA + 2;
   static constexpr int kOffMisc = kOffBar + kNumBars * 8;
   static constexpr int kSmemBytes = kOffMisc + 16;
   static_assert(kSmemBytes <= 226 * 1024, "shared memory overflow");
@@ -554,6 +554,7 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   uint64_t* bar_afull = bar_xempty + AS;
   uint64_t* bar_aempty = bar_afull + TA;
   uint64_t* bar_dfull = bar_aempty + TA;
+  uint64_t* bar_zero = bar_dfull + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kOffMisc);
 
   const int warp = threadIdx.x >> 5;
@@ -582,7 +583,8 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     for (int i = 0; i < WS; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 8); }
     for (int i = 0; i < AS; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
     for (int i = 0; i < TA; ++i) { mbar_init(&bar_afull[i], 8); mbar_init(&bar_aempty[i], 1); }
-    mbar_init(bar_dfull, 1);
+    mbar_init(bar_dfull, 2);  // two MMA issuers
+    mbar_init(bar_zero, 8);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::kTmemCols>(s_tmem);
@@ -628,13 +630,16 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         if (++s == AS) { s = 0; if (it >= AS) ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  } else if (warp == 1 || warp == 11) {
+    // ===================================== two MMA issuers (even / odd stages), accumulators zero-filled up front ==============
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_i8(kBM, NT, 1u, 1u);
-      int sa = 0, sx = 0;
-      uint32_t pha = 0, phx = 0;
-      for (int it = 0; it < n_kb; ++it) {
+      const int first = (warp == 1) ? 0 : 1;
+      int sa = first % TA, sx = first % AS;
+      uint32_t pha = (first / TA) & 1, phx = (first / AS) & 1;
+      mbar_wait(bar_zero, 0);
+      tc_fence_after();
+      for (int it = first; it < n_kb; it += 2) {
         mbar_wait(&bar_afull[sa], pha);
         mbar_wait(&bar_xfull[sx], phx);
         if (it == 0) QS_PROF(4);
@@ -644,25 +649,37 @@ gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
           const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + sx * C::kActBytes + u * C::kActSub));
 #pragma unroll
           for (int t = 0; t < kBK / 32; ++t) {
-            const uint32_t acc = (it > 0 || u > 0 || t > 0) ? 1u : 0u;
             const uint32_t a0 = tmem_base + 2 * NT + sa * C::kAStageCols + u * (kBK / 4) + t * 8;
-            umma_i8_ts(tmem_base, a0, bdesc + t * 2, idesc, acc);
-            if (nb > 4) umma_i8_ts(tmem_base + NT, a0 + kSub * (kBK / 4), bdesc + t * 2, idesc, acc);
+            umma_i8_ts(tmem_base, a0, bdesc + t * 2, idesc, 1u);
+            if (nb > 4) umma_i8_ts(tmem_base + NT, a0 + kSub * (kBK / 4), bdesc + t * 2, idesc, 1u);
           }
         }
         umma_commit(&bar_aempty[sa]);
         umma_commit(&bar_xempty[sx]);
-        if (++sa == TA) { sa = 0; pha ^= 1; }
-        if (++sx == AS) { sx = 0; phx ^= 1; }
+        sa += 2; if (sa >= TA) { sa -= TA; pha ^= 1; }
+        sx += 2; if (sx >= AS) { sx -= AS; phx ^= 1; }
       }
-      umma_commit(bar_dfull);
-      QS_PROF(6);
+      if (n_kb > first) umma_commit(bar_dfull); else mbar_arrive(bar_dfull);
+      if (first == 0) QS_PROF(6);
     }
   } else if (warp >= 2 && warp <= 9) {
     // ===================================== unpack + TMEM epilogue warps: 2..5 serve accumulator 0, 6..9 accumulator 1 ==========
     const int quad = warp & 3;
     const int h = (warp >= 6) ? 1 : 0;
     const int epi_tid = quad * 32 + lane;
+    {
+      // zero-fill this quadrant of accumulator h (all MMAs accumulate)
+      const uint32_t tz = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + h * NT;
+#pragma unroll
+      for (int c = 0; c < NT; c += 8) {
+        tmem_st_16x128b_x2(tz + c, 0u, 0u, 0u, 0u);
+        tmem_st_16x128b_x2(tz + c + (16u << 16), 0u, 0u, 0u, 0u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_zero);
+    }
     {
       int s = 0, ta = 0;
       uint32_t ph = 0, pha = 0;
