@@ -42,9 +42,10 @@ def make(seed, N, K, group):
     if group == -1:
         z = rng.integers(0, 16, size=(N,)).astype(np.int64)
         w = (q - z[:, None]).astype(np.float32) * s1.astype(np.float32)[:, None]
+        w_in = w.copy()  # from_linear quantises linear.weight.data in place
         lin.weight.data = torch.from_numpy(w)
         ql = cls.from_linear(lin, 4, -1, s1_scale=torch.from_numpy(s1), zeros=torch.from_numpy(z).to(torch.int8))
-        out = dict(q=q.astype(np.uint8), s1=s1, z=z, qweight=ql.qweight.numpy(), s1_scales=ql.s1_scales.numpy(),
+        out = dict(q=q.astype(np.uint8), s1=s1, z=z, w=w_in, qweight=ql.qweight.numpy(), s1_scales=ql.s1_scales.numpy(),
                    s1_szeros=ql.s1_szeros.numpy())
     else:
         G = K // group
@@ -52,11 +53,12 @@ def make(seed, N, K, group):
         z = rng.integers(0, 16, size=(N, G)).astype(np.int64)
         w8 = (q.reshape(N, G, group) - z[:, :, None]) * s2[:, :, None]
         w = w8.reshape(N, K).astype(np.float32) * s1.astype(np.float32)[:, None]
+        w_in = w.copy()  # from_linear quantises linear.weight.data in place
         lin.weight.data = torch.from_numpy(w)
         ql = cls.from_linear(lin, 4, group, s1_scale=torch.from_numpy(s1),
                              s2_scale=torch.from_numpy(s2.astype(np.float16)),
                              zeros=torch.from_numpy(z).to(torch.int8))
-        out = dict(q=q.astype(np.uint8), s1=s1, s2=s2, z=z, qweight=ql.qweight.numpy(),
+        out = dict(q=q.astype(np.uint8), s1=s1, s2=s2, z=z, w=w_in, qweight=ql.qweight.numpy(),
                    s1_scales=ql.s1_scales.numpy(), s2_scales=ql.s2_scales.numpy(), s2_zeros=ql.s2_zeros.numpy())
     return out
 

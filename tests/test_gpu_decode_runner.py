@@ -39,3 +39,41 @@ def test_hidden_state_is_finite(dev):
     torch.cuda.synchronize()
     assert tok.shape == (8,)
     assert torch.isfinite(run.out_buf.float()).all()
+
+
+@pytest.mark.parametrize("precision,group", [("w4a8kv4", -1), ("w4a8kv4-g128", 128)])
+def test_converted_checkpoint_loads_and_runs(dev, precision, group):
+    """fake-quant checkpoint -> convert -> fuse -> load_into_runner -> the runner's qkv GEMM equals the oracle GEMM on the
+    converted buffers (bit-exact), and a decode step runs."""
+    import numpy as np
+    from oracle import ops, w4a8
+    from qserve_b200 import checkpoint as ck
+    from qserve_b200.decode import MODELS, DecodeRunner
+    from tests.test_checkpoint import _fake_checkpoint
+    from tests.util import bits16, np_of, to_dev
+    cfg = MODELS["tiny"]
+    fake, params = _fake_checkpoint(cfg.layers, cfg.hidden, cfg.intermediate, cfg.heads, cfg.kv_heads, cfg.head_dim, group, seed=3)
+    fake["model.embed_tokens.weight"] = torch.randn(cfg.vocab, cfg.hidden).half()
+    fake["lm_head.weight"] = torch.randn(cfg.vocab, cfg.hidden).half()
+    sd = ck.convert_fake_quant_checkpoint(fake, params, cfg.layers, 4, group)
+    fused = ck.fuse_llama_state_dict(sd, cfg.layers)
+    run = DecodeRunner("tiny", precision, batch=4, ctx=70, device=dev, seed=1)
+    n = ck.load_into_runner(run, fused)
+    assert n >= cfg.layers * 4 * 3 + 3
+    pre = "model.layers.0.self_attn.qkv_proj."
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((4, cfg.hidden)).astype(np.float16)
+    aq, sa, asum = ops.quant_per_token(x)
+    out = torch.empty((4, fused[pre + "qweight"].size(0)), dtype=torch.half, device=dev)
+    run.layers[0]["qkv"](to_dev(aq, dev), to_dev(sa, dev), to_dev(asum, dev), out)
+    torch.cuda.synchronize()
+    if group == -1:
+        want = w4a8.gemm_w4a8_per_chn(aq, fused[pre + "qweight"].numpy(), fused[pre + "s1_scales"].numpy(), sa, fused[pre + "s1_szeros"].numpy(), asum)
+    else:
+        want = w4a8.gemm_w4a8_per_group(aq, fused[pre + "qweight"].numpy(), fused[pre + "s2_zeros"].numpy(), fused[pre + "s2_scales"].numpy(),
+                                        fused[pre + "s1_scales"].numpy(), sa)
+    assert np.array_equal(bits16(np_of(out)), bits16(want))
+    with torch.no_grad():
+        tok = run.forward(run.tokens_in)
+    torch.cuda.synchronize()
+    assert tok.shape == (4,) and int(tok.min()) >= 0 and int(tok.max()) < cfg.vocab
