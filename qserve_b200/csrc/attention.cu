@@ -5,15 +5,15 @@
 //           kernels/csrc/fused_attention/applyBiasRopeUpdateKVCache.h:94-455 (prefill append),
 //           kernels/csrc/fused_attention/input_metadata_helper.cu:11-45.
 //
-// B200 design (DESIGN.md "Decode attention"): the reference launches one CTA per *query* head and therefore streams
-// every KV head Hq/Hkv times; here one CTA owns a (sequence, KV head, context split) and serves all query heads of the
-// GQA group from a single pass over the 4-bit pages, so HBM traffic is the algorithmic minimum.  Pages are read with
-// 128-bit (K) / 64-bit (V) fully-coalesced vector loads, one 16-token chunk per warp iteration, software-prefetched one
-// chunk ahead.  Codes are expanded in registers with the exact fp16 arithmetic of the reference's dequantiser
-// (magic-number int4->fp16, then one fp16 FMA with the per-token scale and -scale*zero) directly into mma.sync
-// m16n8k16 operand fragments: the tiny (<= 8 heads) x 16-token QK^T and PV products run on the tensor pipe with fp32
-// accumulation, the softmax is an online (flash-decoding) softmax reduced with warp shuffles, and context splits are
-// merged by the last-arriving CTA.  RoPE of q/k, KV quantisation and the page append of the new token are fused in.
+// B200 design: the reference launches one CTA per *query* head and therefore streams every KV head
+// Hq/Hkv times; here one CTA (4 warps) owns a (sequence, KV head, context split) and serves all query heads of the GQA
+// group from a single pass over the pages, so HBM traffic is the algorithmic minimum.  Every warp streams its own 32-token
+// slices of the pages with cp.async.bulk into a private shared-memory ring; the (<= 8 heads) x 32-token QK^T and PV
+// products run as mma.sync m16n8k16 on "biased" operands (0x6400 | code = 1024 + code in fp16: one LOP3 per two codes, the
+// constant parts are removed after the MMA), per-token scale / zero are folded into the logits and probabilities, the
+// softmax is an online (flash-decoding) softmax with lazy rescaling, and context splits are merged by the last-arriving
+// CTA.  RoPE of q/k, KV quantisation and the page append of the new token are fused in; optionally also the per-token
+// INT8 quantisation of the output row (single_query_attention_quant).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -72,15 +72,16 @@ __device__ __forceinline__ uint32_t kv_quant_code(float x, float inv_s, float z)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: decode attention, TMA-staged (v2)
-//   stage = one 64-token page of one kv head: K codes | V codes | K scales | K zeros | V scales | V zeros, brought into
-//   shared memory by six cp.async.bulk copies issued by a dedicated producer warp (4-deep ring, mbarrier full/empty).
-//   Consumer warp w owns tokens [16w, 16w+16) of every page.
+// K1: decode attention
+//   Warp w consumes the 32-token slice (w & 1) of the pages of parity (w >> 1) of its CTA's context range.
 //   Scale folding (exact in real arithmetic; skips the reference's per-element fp16 rounding of the dequantised values):
-//     q.k_t   = s_t * (q . u_t) + c_t * sum(q)          u = raw integer codes as fp16,   c_t = half(-s_t * z_t)
+//     q.k_t   = s_t * (q . u_t) + c_t * sum(q)          u = integer codes,   c_t = half(-s_t * z_t)
 //     sum_t p_t v_t = sum_t (p_t s_t) u_t + sum_t p_t c_t
-//   so the tensor-core operands are the raw codes and the per-token scale touches 4 logits / 4 probabilities per thread
-//   instead of 2 x 128 elements.  (KV8: k_t = s_t * (u_t - z_t), same folding with c_t = -s_t * z_t in fp32.)
+//   so the per-token scale touches 4 logits / 4 probabilities per thread instead of 2 x 128 elements
+//   (KV8: k_t = s_t * (u_t - z_t), same folding with c_t = -s_t * z_t in fp32).
+//   Biased operands: the MMA sees 1024 + u (low nibble / byte) or 1024 + 16 u (high nibble; Q pre-scaled by 1/16 on the K
+//   side, output rows rescaled at the end on the V side); sum_d (1024 + w_d u_d) q'_d = B(q) + sum_d u_d q_d with B(q) computed
+//   once per head, and sum_t p'_t (1024 + u_t) = 1024 sum_t p'_t + ... with sum_t p'_t from one MMA against an all-ones tile.
 // ------------------------------------------------------------------------------------------------
 constexpr int kAttnConsumers = 128;
 constexpr int kAttnThreadsV2 = kAttnConsumers;  // no dedicated producer warp: every warp streams its own half pages

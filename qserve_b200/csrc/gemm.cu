@@ -14,16 +14,19 @@
 //     reference's exact 32-bit multiply + vadd4), and write INT8 rows straight into TENSOR MEMORY with
 //     tcgen05.st.16x128b -- the mma.sync B-fragment order of the checkpoint is exactly the 16x128b TMEM store
 //     pattern, so no shuffle and no shared-memory round trip is needed.
-//   * one elected thread issues tcgen05.mma.kind::i8 with A (weights) from TMEM and B (INT8 activations, TMA-loaded
-//     with the 128-byte swizzle) from shared memory; INT32 accumulators live in TMEM.
+//   * two issuer threads (warps 1 and 7: even / odd 256-K stages) issue tcgen05.mma.kind::i8 with A (weights) from TMEM and
+//     B (INT8 activations, TMA-loaded with the 128-byte swizzle) from shared memory; INT32 accumulators live in TMEM and are
+//     zero-filled up front so that every MMA accumulates (the integer result cannot depend on how the two streams interleave).
+//   * weights and activations travel in separate rings: the weight producer never waits for the previous kernel, so with
+//     programmatic dependent launch the ring and the unpacked TMEM stages fill while the preceding norm / quant kernel runs.
 //   * decode shapes have too few 128-channel tiles to fill 148 SMs, so K is split across a thread-block CLUSTER
 //     (2/4/8 CTAs); the INT32 partial tiles are reduced through DISTRIBUTED SHARED MEMORY (each CTA sums and finishes
 //     a 1/S slice of the channels) -- integer adds, so the result is bit-identical for every split.
-//   * two CTAs per SM (<= 110 KB smem, 256 TMEM columns each) so one CTA's prologue / epilogue overlaps the other's
+//   * two CTAs per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's prologue / epilogue overlaps the other's
 //     weight stream.
-//   * epilogue fused: acc*s1[n]*sa[m] - s1z[n]*asum[m] (per-channel) or acc*(s1[n]*sa[m]) (per-group, W8A8) -> fp16.
-//   * programmatic dependent launch: the weight prefetch is issued before griddepcontrol.wait, so HBM keeps streaming
-//     while the preceding activation-quant kernel drains.
+//   * epilogue fused: acc*s1[n]*sa[m] - s1z[n]*asum[m] (per-channel) or acc*(s1[n]*sa[m]) (per-group, W8A8) -> fp16,
+//     IEEE fp32 in the reference's source order (bit-exact against the oracle).
+//   * gemm_wide_kernel (opt-in): a band-partitioned one-CTA-per-SM variant for layers with more tiles than SMs.
 #include <cstdarg>
 #include <cstdio>
 
