@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Launch the prefill-sized per-channel GEMM (M tokens through gate_up_proj of Llama-3-8B) a few times -- target for the
+tensor-pipe utilisation capture (`ncu --set full -k regex:gemm_kernel`)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qserve_backend.qgemm_w4a8_per_chn as op  # noqa: E402
+
+M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+N, K = 28672, 4096
+dev = torch.device("cuda:0")
+g = torch.Generator(device="cpu").manual_seed(0)
+a = torch.randint(-127, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
+w = torch.randint(-128, 128, (N, K // 2), dtype=torch.int8, generator=g).to(dev)
+s1 = torch.full((N,), 0.01, dtype=torch.half, device=dev)
+sa = torch.full((M,), 0.01, dtype=torch.half, device=dev)
+out = torch.empty((M, N), dtype=torch.half, device=dev)
+for _ in range(4):
+    op.gemm_forward_cuda(a, w, s1, sa, s1, sa, out)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    op.gemm_forward_cuda(a, w, s1, sa, s1, sa, out)
+e1.record()
+torch.cuda.synchronize()
+t = e0.elapsed_time(e1) / 10 * 1e-3
+print(f"M={M} N={N} K={K}: {t * 1e6:.1f} us, {2.0 * M * N * K / t / 1e12:.0f} INT8 TOP/s")
