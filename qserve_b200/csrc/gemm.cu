@@ -92,6 +92,13 @@ struct Cfg {
   static constexpr int kNumBars = 2 * WS + 2 * kActStages + 2 * (kTA > 0 ? kTA : 1) + 2;
   static constexpr int kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr
   static constexpr int kSmemBytes = kOffMisc + 16;
+  // split-K (cluster) launches append a dedicated receive buffer: every CTA pushes its INT32 partials of the channels another
+  // CTA of the cluster finishes straight into that CTA's buffer (posted st.shared::cluster from the TMEM-load registers); the
+  // owner then sums S local rows.  Such launches run one CTA per SM (the buffer does not fit next to a second CTA).
+  static constexpr int kOffRx = (kSmemBytes + 127) / 128 * 128;
+  static constexpr int kRxBytes = NT * kBM * 4;  // [sender][token][128 / S channels]
+  static constexpr int kSmemBytesSplit = kOffRx + kRxBytes;
+  static constexpr bool kSplitFits = kSmemBytesSplit <= 226 * 1024;
   // two co-resident CTAs per SM when both the TMEM columns (<= 256 each) and the shared memory (<= 113 KB each) allow it
   static constexpr int kCtasPerSm = (kTmemCols <= 256 && kSmemBytes <= 113 * 1024) ? 2 : 1;
   static_assert(kSmemBytes <= 226 * 1024, "shared memory overflow");
@@ -117,10 +124,8 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ int2 ld_dsmem_v2(uint32_t addr) {
-  int2 v;
-  asm volatile("ld.shared::cluster.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-  return v;
+__device__ __forceinline__ void st_dsmem_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // INT32 -> FP32, round to nearest even, WITHOUT the conversion unit (I2F issues once per 16 cycles per SM sub-partition on the
@@ -387,15 +392,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
     mbar_wait(bar_dfull, 0);   // all MMAs retired: accumulators complete, pipeline buffers free
     tc_fence_after();
     if (epi_tid == 0) QS_PROF(8);
-    // TMEM -> shared memory, transposed to [token][channel] so that channel pairs are contiguous
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    if (S == 1) {
+      // TMEM -> shared memory, transposed to [token][channel] so that channel pairs are contiguous
 #pragma unroll 1
-    for (int c = 0; c < NT / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(trow + c * 32, r);
-      tmem_wait_ld();
+      for (int c = 0; c < NT / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(trow + c * 32, r);
+        tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) s_red[(c * 32 + i) * kBM + epi_tid] = static_cast<int32_t>(r[i]);
+        for (int i = 0; i < 32; ++i) s_red[(c * 32 + i) * kBM + epi_tid] = static_cast<int32_t>(r[i]);
+      }
+    } else {
+      // TMEM -> the receive buffer of the CTA that finishes this channel: rx[sender = rank][token][channel % (128 / S)].
+      // Posted remote stores (>= 64 contiguous bytes per warp instruction); the cluster barrier below publishes them.
+      const int cps = kBM / S;  // channels finished per CTA
+      const uint32_t owner = static_cast<uint32_t>(epi_tid / cps);
+      const uint32_t rx_peer = map_to_cta(smem_u32(smem + C::kOffRx), owner) + static_cast<uint32_t>(((rank * NT) * cps + (epi_tid % cps)) * 4);
+#pragma unroll 1
+      for (int c = 0; c < NT / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(trow + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) st_dsmem_u32(rx_peer + static_cast<uint32_t>((c * 32 + i) * cps * 4), r[i]);
+      }
     }
     if (epi_tid == 0) QS_PROF(9);
   } else {
@@ -411,7 +432,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
     const int tid = threadIdx.x;
     if (tid == 0) QS_PROF(10);
     const int m0 = m_tile * NT;
-    const uint32_t red_local = smem_u32(s_red);
     // npairs divides 256, so a thread keeps one channel pair and walks the tokens
     const int tstep = kNumThreads / npairs;    // 4 * S tokens are finished per pass of the CTA
     const int n = n_tile * kBM + 2 * pr;
@@ -445,58 +465,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
         }
       }
     } else {
-      uint32_t red_peer[8];
+      // S > 1: the partials of all S senders sit in this CTA's receive buffer; sum them locally
+      const int cps = kBM / S;
+      const int32_t* rx = reinterpret_cast<const int32_t*>(smem + C::kOffRx);
+      const int prl = tid % npairs;  // channel pair inside this CTA's slice
+      const int tpt = NT / (4 * S);  // tokens of this thread
+#pragma unroll 1
+      for (int i = 0; i < tpt; ++i) {
+        const int tok = tok0 + i * tstep;
+        int2 acc = make_int2(0, 0);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) red_peer[r] = (r < S) ? map_to_cta(red_local, r) : red_local;
-      const int tpt = NT / (4 * S);                 // tokens of this thread
-      const int per_round = S == 2 ? 8 : S == 4 ? 4 : 2;   // 16 / S tokens per round
-      for (int i0 = 0; i0 < tpt; i0 += per_round) {
-        if (S == 2) {
-          int2 v[8][2];
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) v[e][r] = (i0 + e < tpt) ? ld_dsmem_v2(red_peer[r] + off0 + (i0 + e) * off_step) : make_int2(0, 0);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int tok = tok0 + (i0 + e) * tstep;
-            if (i0 + e < tpt && tok < tok_end) finish(tok, make_int2(v[e][0].x + v[e][1].x, v[e][0].y + v[e][1].y), optr + (i0 + e) * ostep);
-          }
-        } else if (S == 4) {
-          int2 v[4][4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) v[e][r] = (i0 + e < tpt) ? ld_dsmem_v2(red_peer[r] + off0 + (i0 + e) * off_step) : make_int2(0, 0);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int tok = tok0 + (i0 + e) * tstep;
-            int2 acc = make_int2(0, 0);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { acc.x += v[e][r].x; acc.y += v[e][r].y; }
-            if (i0 + e < tpt && tok < tok_end) finish(tok, acc, optr + (i0 + e) * ostep);
-          }
-        } else {
-          int2 v[2][8];
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[e][r] = (i0 + e < tpt) ? ld_dsmem_v2(red_peer[r] + off0 + (i0 + e) * off_step) : make_int2(0, 0);
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int tok = tok0 + (i0 + e) * tstep;
-            int2 acc = make_int2(0, 0);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) { acc.x += v[e][r].x; acc.y += v[e][r].y; }
-            if (i0 + e < tpt && tok < tok_end) finish(tok, acc, optr + (i0 + e) * ostep);
+        for (int r = 0; r < 8; ++r) {
+          if (r < S) {
+            const int2 v = *reinterpret_cast<const int2*>(rx + (r * NT + tok) * cps + 2 * prl);
+            acc.x += v.x; acc.y += v.y;
           }
         }
+        if (tok < tok_end) finish(tok, acc, optr + i * ostep);
       }
     }
     if (tid == 0) QS_PROF(11);
   }
-  // no CTA may exit (and free its shared memory) while peers are still reading it
-  if (S > 1) cluster_sync_all(); else __syncthreads();
+  // S > 1: every remote store into this CTA's receive buffer was ordered before the cluster barrier above; none follows
+  __syncthreads();
   if (threadIdx.x == 0) QS_PROF(12);
   qs_trace(QS_K_GEMM, 2);
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
@@ -859,6 +850,8 @@ int choose_split(int tiles, int kb_per_tile, int forced) {
   }
   if (s > 8) s = 8;
   while (s > 1 && kb_per_tile < s) s /= 2;
+  // split launches carry a receive buffer and run one CTA per SM: never more CTAs than SMs (a second wave costs more than it saves)
+  if (forced <= 0) while (s > 1 && tiles * s > num_sms()) s /= 2;
   return s;
 }
 
@@ -880,7 +873,7 @@ int launch_gemm(const GemmArgs& a) {
   p.m_tiles = (a.M + NT - 1) / NT;
   p.kb_per_tile = (a.K + kSub * kBK - 1) / (kSub * kBK);  // pipeline stages of 256 K (the last one may be half zero-filled)
   const int tiles = n_tiles * p.m_tiles;
-  p.split = choose_split(tiles, p.kb_per_tile, a.force_split);
+  p.split = C::kSplitFits ? choose_split(tiles, p.kb_per_tile, a.force_split) : 1;  // NT = 256: no room for the receive buffer
 
   CUtensorMap tm_act, tm_w;
   int rc = make_tmap_u8(&tm_act, a.act, a.M, a.K, NT);
@@ -891,14 +884,15 @@ int launch_gemm(const GemmArgs& a) {
   auto kern = a.acc_out ? gemm_kernel<MODE, NT, WS, AS, true> : gemm_kernel<MODE, NT, WS, AS, false>;
   static bool attr_set[2] = {false, false};
   if (!attr_set[a.acc_out ? 1 : 0]) {
-    rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "cudaFuncSetAttribute(gemm smem)");
+    rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSplitFits ? C::kSmemBytesSplit : C::kSmemBytes),
+                    "cudaFuncSetAttribute(gemm smem)");
     if (rc) return rc;
     attr_set[a.acc_out ? 1 : 0] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles * p.split);
   cfg.blockDim = dim3(kNumThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.dynamicSmemBytes = p.split > 1 ? C::kSmemBytesSplit : C::kSmemBytes;
   cfg.stream = static_cast<cudaStream_t>(a.stream);
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
