@@ -20,8 +20,9 @@
 //   * weights and activations travel in separate rings: the weight producer never waits for the previous kernel, so with
 //     programmatic dependent launch the ring and the unpacked TMEM stages fill while the preceding norm / quant kernel runs.
 //   * decode shapes have too few 128-channel tiles to fill 148 SMs, so K is split across a thread-block CLUSTER
-//     (2/4/8 CTAs); the INT32 partial tiles are reduced through DISTRIBUTED SHARED MEMORY (each CTA sums and finishes
-//     a 1/S slice of the channels) -- integer adds, so the result is bit-identical for every split.
+//     (2/4/8 CTAs); every CTA pushes its INT32 partials of the channels a peer finishes into that peer's receive buffer
+//     through DISTRIBUTED SHARED MEMORY (st.shared::cluster) and each CTA sums and finishes a 1/S slice of the channels --
+//     integer adds, so the result is bit-identical for every split.  Split launches run one CTA per SM.
 //   * two CTAs per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's prologue / epilogue overlaps the other's
 //     weight stream.
 //   * epilogue fused: acc*s1[n]*sa[m] - s1z[n]*asum[m] (per-channel) or acc*(s1[n]*sa[m]) (per-group, W8A8) -> fp16,
