@@ -846,8 +846,6 @@ int choose_split(int tiles, int kb_per_tile, int forced) {
     const int sms = num_sms();
     // smallest power of two that brings the CTA count to >= ~2/3 of the SMs; every CTA keeps >= 2 k-blocks
     while (s < 8 && tiles * s < (2 * sms) / 3 && kb_per_tile / (2 * s) >= 1) s *= 2;
-    // long-K layers (down_proj): one more doubling while every CTA still streams >= 6 stages -- more bytes in flight per SM
-    if (s == 4 && tiles * s < sms && kb_per_tile / 8 >= 6) s = 8;
   }
   if (s > 8) s = 8;
   while (s > 1 && kb_per_tile < s) s /= 2;
