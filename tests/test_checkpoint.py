@@ -123,3 +123,39 @@ def test_convert_rejects_inconsistent_group_metadata():
     fake, params = _fake_checkpoint(1, 128, 256, 1, 1, 128, -1)
     with pytest.raises(ValueError):
         ck.convert_fake_quant_checkpoint(fake, params, num_layers=1, w_bit=4, group_size=128)
+
+
+# ---- property tests (hypothesis): layout identities that must hold for every shape ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(n32=st.integers(1, 6), k32=st.integers(1, 8), seed=st.integers(0, 2**31 - 1))
+def test_pack_unpack_is_a_bijection_for_every_shape(n32, k32, seed):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randint(0, 16, (32 * n32, 32 * k32), generator=g, dtype=torch.int16)
+    packed = ck.pack_int4(q)
+    assert packed.shape == (32 * n32, 16 * k32) and packed.dtype == torch.int8
+    assert torch.equal(ck.unpack_int4(packed).to(torch.int16), q)
+    # one 32x32 tile is one contiguous 512-byte block: changing a single code touches exactly one byte of that block
+    q2 = q.clone()
+    r, c = int(seed % (32 * n32)), int((seed // 7) % (32 * k32))
+    q2[r, c] = (q2[r, c] + 1) % 16
+    diff = (ck.pack_int4(q2) != packed).reshape(n32, k32, 512).nonzero()
+    assert diff.shape[0] == 1 and int(diff[0, 0]) == r // 32 and int(diff[0, 1]) == c // 32
+
+
+@settings(max_examples=15, deadline=None)
+@given(tiles_n=st.integers(1, 3), blocks_k=st.integers(1, 3), size=st.sampled_from([1, 2, 4]), seed=st.integers(0, 2**31 - 1))
+def test_row_and_column_shards_tile_the_unsharded_weight(tiles_n, blocks_k, size, seed):
+    """tp.shard_rows / shard_columns on the packed layout == slicing the unpacked code matrix (any TP size)."""
+    from qserve_b200 import tp
+    N, K = 128 * size * tiles_n, 128 * size * blocks_k
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int16)
+    packed = ck.pack_int4(q)
+    for r in range(size):
+        cols = ck.unpack_int4(tp.shard_columns(packed, r, size)).to(torch.int16)
+        assert torch.equal(cols, q[r * N // size:(r + 1) * N // size])
+        rows = ck.unpack_int4(tp.shard_rows(packed, r, size)).to(torch.int16)
+        assert torch.equal(rows, q[:, r * K // size:(r + 1) * K // size])
