@@ -338,3 +338,37 @@ def decode_attention(q, k, v, kpool: PagePool, vpool: PagePool, block_tables, le
                 active = mid
             out[b, h] = acc[0].astype(np.float16)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+#  prefill attention: what `flash_attn_varlen_func(q, k, v, cu_seqlens, ..., causal=True)` computes at
+# llama_w4a8_unpad.py:232 on the rotated q / k of the packed qkv buffer -- un-quantised K / V, causal, grouped-query.
+# Reference for the B200 prefill kernel of the next round; float64, no rounding model (flash-attn is third-party and unpinned).
+# ------------------------------------------------------------------------------------------------
+
+
+def prefill_attention(qkv, cu_seqlens, num_heads: int, num_kv_heads: int, head_dim: int = 128):
+    """qkv fp16 [T, (Hq+2Hkv)*D] (q and k already rotated by `prefill_rope_append`), cu_seqlens int [B+1]
+    -> out float64 [T, Hq*D]: softmax(q k^T / sqrt(D), causal within each sequence) v, query head h reads kv head h // (Hq/Hkv)."""
+    qkv = np.asarray(qkv, dtype=np.float64)
+    T = qkv.shape[0]
+    Hq, Hkv, D = num_heads, num_kv_heads, head_dim
+    G = Hq // Hkv
+    q = qkv[:, : Hq * D].reshape(T, Hq, D)
+    k = qkv[:, Hq * D: (Hq + Hkv) * D].reshape(T, Hkv, D)
+    v = qkv[:, (Hq + Hkv) * D:].reshape(T, Hkv, D)
+    out = np.zeros((T, Hq, D))
+    cu = np.asarray(cu_seqlens, np.int64)
+    for b in range(len(cu) - 1):
+        s, e = int(cu[b]), int(cu[b + 1])
+        L = e - s
+        if L == 0:
+            continue
+        mask = np.tril(np.ones((L, L), dtype=bool))
+        for h in range(Hq):
+            logits = (q[s:e, h] @ k[s:e, h // G].T) / np.sqrt(D)
+            logits = np.where(mask, logits, -np.inf)
+            p = np.exp(logits - logits.max(axis=1, keepdims=True))
+            p /= p.sum(axis=1, keepdims=True)
+            out[s:e, h] = p @ v[s:e, h // G]
+    return out.reshape(T, Hq * D)

@@ -149,3 +149,30 @@ def test_prefill_then_decode_consistency(rng):
     assert np.array_equal(kp2.codes()[2, :, 3], kp.codes()[2, :, 3])
     assert np.array_equal(vp2.codes()[2, :, 3], vp.codes()[2, :, 3])
     assert np.array_equal(kp2.scales()[2, :, 3].view(np.uint16), kp.scales()[2, :, 3].view(np.uint16))
+
+
+def test_prefill_attention_reference_properties(rng):
+    """The prefill-attention restatement (next scope row): agrees with torch SDPA per sequence, is causal, and its last row
+    equals single-query attention over the un-quantised keys of the same sequence."""
+    import torch
+    Hq, Hkv, D = 4, 2, 128
+    lens = [5, 1, 9]
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    T = int(cu[-1])
+    qkv = rng.standard_normal((T, (Hq + 2 * Hkv) * D)).astype(np.float16)
+    out = kv.prefill_attention(qkv, cu, Hq, Hkv, D).reshape(T, Hq, D)
+    q = torch.from_numpy(qkv[:, : Hq * D].astype(np.float64)).reshape(T, Hq, D)
+    k = torch.from_numpy(qkv[:, Hq * D:(Hq + Hkv) * D].astype(np.float64)).reshape(T, Hkv, D)
+    v = torch.from_numpy(qkv[:, (Hq + Hkv) * D:].astype(np.float64)).reshape(T, Hkv, D)
+    for b, L in enumerate(lens):
+        s, e = int(cu[b]), int(cu[b + 1])
+        kk = k[s:e].repeat_interleave(Hq // Hkv, dim=1).transpose(0, 1)
+        vv = v[s:e].repeat_interleave(Hq // Hkv, dim=1).transpose(0, 1)
+        ref = torch.nn.functional.scaled_dot_product_attention(q[s:e].transpose(0, 1), kk, vv, is_causal=True).transpose(0, 1).numpy()
+        assert np.abs(out[s:e] - ref).max() < 1e-9
+    # causality: perturbing a later token of a sequence leaves the earlier rows untouched
+    qkv2 = qkv.copy()
+    qkv2[int(cu[3]) - 1] += 1
+    out2 = kv.prefill_attention(qkv2, cu, Hq, Hkv, D).reshape(T, Hq, D)
+    assert np.array_equal(out2[: int(cu[3]) - 1], out[: int(cu[3]) - 1])
+    assert not np.array_equal(out2[int(cu[3]) - 1], out[int(cu[3]) - 1])
