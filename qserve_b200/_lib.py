@@ -38,6 +38,8 @@ SIGNATURES = {
     "qs_invoke_quant": (c_int, [_P, _P, _P, _I, _I, _P]),
     "qs_invoke_quant_scalar": (c_int, [_P, _P, _F, _I, _I, _P]),
     "qs_invoke_quant_fuse_sum": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "qs_row_absmax": (c_int, [_P, _P, _I, _I, _P]),
+    "qs_invoke_quant_given_amax": (c_int, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "qs_invoke_dequant_add_residual": (c_int, [_P, _P, _P, _P, _F, _I, _I, _P]),
     "qs_invoke_dequant": (c_int, [_P, _P, _F, _I, _I, _I, _I, _P]),
     "qs_silu_and_mul": (c_int, [_P, _P, _I, _I, _P]),

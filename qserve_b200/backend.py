@@ -22,8 +22,16 @@ _HALF = torch.float16
 # --------------------------------------------------------------------------------------------------
 
 
-def _stream(t: torch.Tensor) -> int:
-    return torch._C._cuda_getCurrentRawStream(t.device.index if t.device.index is not None else torch.cuda.current_device())
+def _call(t: torch.Tensor, fn, *args) -> None:
+    """Launch `fn(*args, stream)` on the current stream of t's device, with that device current (the reference ops hold an
+    at::cuda::CUDAGuard on the input's device, fused_attention.cpp:203); raises RuntimeError on failure."""
+    idx = t.device.index
+    cur = torch.cuda.current_device()
+    if idx is None or idx == cur:
+        check(fn(*args, torch._C._cuda_getCurrentRawStream(cur)))
+    else:
+        with torch.cuda.device(idx):
+            check(fn(*args, torch._C._cuda_getCurrentRawStream(idx)))
 
 
 def _require(cond: bool, msg: str) -> None:
@@ -36,6 +44,7 @@ def _cuda(t: torch.Tensor, name: str) -> None:
 
 
 _workspaces: dict = {}
+_retired: list = []  # outgrown workspaces, kept alive for graphs captured with them
 
 
 def gemm_workspace(device: torch.device) -> torch.Tensor:
@@ -53,7 +62,12 @@ def attention_workspace(device: torch.device, batch: int, num_heads: int, head_d
     need = lib.qs_attention_workspace_bytes(batch, num_heads, head_dim)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
-        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        # a workspace that was handed out is never freed: a captured CUDA graph may still hold its address (the self-cleaning
+        # counters inside must not alias reused memory on replay)
+        if ws is not None:
+            _retired.append(ws)
+        with torch.cuda.device(device):
+            ws = torch.zeros(need, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
@@ -89,9 +103,9 @@ def w4a8_per_chn_gemm_forward_cuda(in_feats, kernel, wscales, ascales, w_szs, a_
     if M == 0:
         return
     ws = gemm_workspace(in_feats.device)
-    check(lib.qs_w4a8_gemm_per_chn(in_feats.data_ptr(), kernel.data_ptr(), wscales.data_ptr(), ascales.data_ptr(), w_szs.data_ptr(),
+    _call(in_feats, lib.qs_w4a8_gemm_per_chn, in_feats.data_ptr(), kernel.data_ptr(), wscales.data_ptr(), ascales.data_ptr(), w_szs.data_ptr(),
                                    a_ssums.data_ptr(), out_feats.data_ptr(), _acc_out.data_ptr() if _acc_out is not None else None,
-                                   M, N, K, ws.data_ptr(), ws.numel(), _stream(in_feats)))
+                                   M, N, K, ws.data_ptr(), ws.numel())
 
 
 def w4a8_per_group_gemm_forward_cuda(in_feats, kernel, zeros, scales_i8, wscales, ascales, out_feats, _acc_out=None) -> None:
@@ -105,9 +119,9 @@ def w4a8_per_group_gemm_forward_cuda(in_feats, kernel, zeros, scales_i8, wscales
     if M == 0:
         return
     ws = gemm_workspace(in_feats.device)
-    check(lib.qs_w4a8_gemm_per_group(in_feats.data_ptr(), kernel.data_ptr(), zeros.data_ptr(), scales_i8.data_ptr(), wscales.data_ptr(),
+    _call(in_feats, lib.qs_w4a8_gemm_per_group, in_feats.data_ptr(), kernel.data_ptr(), zeros.data_ptr(), scales_i8.data_ptr(), wscales.data_ptr(),
                                      ascales.data_ptr(), out_feats.data_ptr(), _acc_out.data_ptr() if _acc_out is not None else None,
-                                     M, N, K, ws.data_ptr(), ws.numel(), _stream(in_feats)))
+                                     M, N, K, ws.data_ptr(), ws.numel())
 
 
 def w8a8_gemm_forward_cuda(in_feats, kernel, wscales, ascales, out_feats, _acc_out=None) -> None:
@@ -117,8 +131,8 @@ def w8a8_gemm_forward_cuda(in_feats, kernel, wscales, ascales, out_feats, _acc_o
     if M == 0:
         return
     ws = gemm_workspace(in_feats.device)
-    check(lib.qs_w8a8_gemm(in_feats.data_ptr(), kernel.data_ptr(), wscales.data_ptr(), ascales.data_ptr(), out_feats.data_ptr(),
-                           _acc_out.data_ptr() if _acc_out is not None else None, M, N, K, ws.data_ptr(), ws.numel(), _stream(in_feats)))
+    _call(in_feats, lib.qs_w8a8_gemm, in_feats.data_ptr(), kernel.data_ptr(), wscales.data_ptr(), ascales.data_ptr(), out_feats.data_ptr(),
+                           _acc_out.data_ptr() if _acc_out is not None else None, M, N, K, ws.data_ptr(), ws.numel())
 
 
 # --------------------------------------------------------------------------------------------------
@@ -155,11 +169,11 @@ def single_query_attention(q, k, v, kv_pointers, length_per_sample_: Optional[to
         _require(tuple(alibi_slopes_.shape) == (nheads,) and alibi_slopes_.dtype == torch.float32, "alibi_slopes must be float32 [nheads]")
     out = torch.empty((q.size(0), nheads, headdim), dtype=q.dtype, device=q.device)
     ws = attention_workspace(q.device, batch, nheads, headdim)
-    check(lib.qs_single_query_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0), kv_pointers.data_ptr(),
+    _call(q, lib.qs_single_query_attention, q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0), kv_pointers.data_ptr(),
                                         lens_ptr, out.data_ptr(), batch, nheads, nheads_kv, headdim, kv_pointers.size(-1), int(memory_max_seqlen),
                                         int(tokens_per_block), int(size_per_token), int(timestep), int(rotary_embedding_dim), float(rotary_base),
                                         int(bool(neox_rotary_style)), int(bool(int4_kv_cache)), int(bool(kv_cache_with_zeros)), ws.data_ptr(),
-                                        ws.numel(), _stream(q)))
+                                        ws.numel())
     return out
 
 
@@ -178,11 +192,11 @@ def apply_bias_rope_update_kv_cache(qkv, seq_lens, padding_offset, kv_pointers: 
     if kv_pointers is not None:
         _require(kv_pointers.is_contiguous() and kv_pointers.dtype == torch.int64, "kv_pointers must be contiguous int64")
         kvp, max_blocks = kv_pointers.data_ptr(), kv_pointers.size(-1)
-    check(lib.qs_apply_bias_rope_update_kv_cache(qkv.data_ptr(), seq_lens.data_ptr(), padding_offset.data_ptr(), kvp, seq_lens.size(0), qkv.size(0),
+    _call(qkv, lib.qs_apply_bias_rope_update_kv_cache, qkv.data_ptr(), seq_lens.data_ptr(), padding_offset.data_ptr(), kvp, seq_lens.size(0), qkv.size(0),
                                                  max_blocks, int(head_num), int(kv_head_num), head_dim, int(seq_len), int(tokens_per_block),
                                                  int(size_per_token), int(rotary_embedding_dim), float(rotary_embedding_base),
                                                  int(rotary_embedding_max_positions), int(bool(neox_rotary_style)), int(bool(int4_kv_cache)),
-                                                 int(bool(kv_cache_with_zeros)), _stream(qkv)))
+                                                 int(bool(kv_cache_with_zeros)))
 
 
 def compute_padding_offsets(cu_seqlens, max_seqlen: int, tot_num_tokens: int) -> torch.Tensor:
@@ -190,7 +204,7 @@ def compute_padding_offsets(cu_seqlens, max_seqlen: int, tot_num_tokens: int) ->
     _cuda(cu_seqlens, "cu_seqlens")
     _require(cu_seqlens.dtype == torch.int32, "cu_seqlens must be int32")
     out = torch.empty((tot_num_tokens,), dtype=torch.int32, device=cu_seqlens.device)
-    check(lib.qs_compute_padding_offsets(out.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.size(0) - 1, int(max_seqlen), _stream(cu_seqlens)))
+    _call(cu_seqlens, lib.qs_compute_padding_offsets, out.data_ptr(), cu_seqlens.data_ptr(), cu_seqlens.size(0) - 1, int(max_seqlen))
     return out
 
 
@@ -219,7 +233,7 @@ def rms_norm(out, input, weight, epsilon: float, use_quant: bool = False) -> Non
     if _noop(input):
         return
     tokens, hidden = _rows(input)
-    check(lib.qs_rms_norm(out.data_ptr(), input.data_ptr(), weight.data_ptr(), float(epsilon), int(bool(use_quant)), tokens, hidden, _stream(input)))
+    _call(input, lib.qs_rms_norm, out.data_ptr(), input.data_ptr(), weight.data_ptr(), float(epsilon), int(bool(use_quant)), tokens, hidden)
 
 
 def rms_norm_general(out, input, weight, scaling, epsilon: float, use_per_token_quant: bool = False) -> None:
@@ -228,8 +242,8 @@ def rms_norm_general(out, input, weight, scaling, epsilon: float, use_per_token_
     if _noop(input):
         return
     tokens, hidden = _rows(input)
-    check(lib.qs_rms_norm_general(out.data_ptr(), input.data_ptr(), weight.data_ptr(), scaling.data_ptr(), float(epsilon),
-                                  int(bool(use_per_token_quant)), tokens, hidden, _stream(input)))
+    _call(input, lib.qs_rms_norm_general, out.data_ptr(), input.data_ptr(), weight.data_ptr(), scaling.data_ptr(), float(epsilon),
+                                  int(bool(use_per_token_quant)), tokens, hidden)
 
 
 def rms_norm_general_fuse_sum(out, input, weight, input_sum, scaling, epsilon: float, use_per_token_quant: bool = False) -> None:
@@ -238,8 +252,8 @@ def rms_norm_general_fuse_sum(out, input, weight, input_sum, scaling, epsilon: f
     if _noop(input):
         return
     tokens, hidden = _rows(input)
-    check(lib.qs_rms_norm_general_fuse_sum(out.data_ptr(), input.data_ptr(), weight.data_ptr(), input_sum.data_ptr(), scaling.data_ptr(),
-                                           float(epsilon), int(bool(use_per_token_quant)), tokens, hidden, _stream(input)))
+    _call(input, lib.qs_rms_norm_general_fuse_sum, out.data_ptr(), input.data_ptr(), weight.data_ptr(), input_sum.data_ptr(), scaling.data_ptr(),
+                                           float(epsilon), int(bool(use_per_token_quant)), tokens, hidden)
 
 
 def invoke_dequant_add_residual_rms_norm_quant(out, input, residual, gamma, scale, epsilon: float) -> None:
@@ -249,12 +263,12 @@ def invoke_dequant_add_residual_rms_norm_quant(out, input, residual, gamma, scal
         return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
-        check(lib.qs_dequant_add_residual_rms_norm_quant(out.data_ptr(), input.data_ptr(), residual.data_ptr(), gamma.data_ptr(), scale.data_ptr(), 0.0,
-                                                         float(epsilon), tokens, hidden, _stream(input)))
+        _call(input, lib.qs_dequant_add_residual_rms_norm_quant, out.data_ptr(), input.data_ptr(), residual.data_ptr(), gamma.data_ptr(), scale.data_ptr(), 0.0,
+                                                         float(epsilon), tokens, hidden)
     else:
         s = float(torch.tensor(float(scale), dtype=_HALF))  # at::Half argument
-        check(lib.qs_dequant_add_residual_rms_norm_quant(out.data_ptr(), input.data_ptr(), residual.data_ptr(), gamma.data_ptr(), None, s,
-                                                         float(epsilon), tokens, hidden, _stream(input)))
+        _call(input, lib.qs_dequant_add_residual_rms_norm_quant, out.data_ptr(), input.data_ptr(), residual.data_ptr(), gamma.data_ptr(), None, s,
+                                                         float(epsilon), tokens, hidden)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -270,10 +284,10 @@ def invoke_quant(out, input, scale) -> None:
         return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
-        check(lib.qs_invoke_quant(out.data_ptr(), input.data_ptr(), scale.data_ptr(), tokens, hidden, _stream(input)))
+        _call(input, lib.qs_invoke_quant, out.data_ptr(), input.data_ptr(), scale.data_ptr(), tokens, hidden)
     else:
         s = float(torch.tensor(float(scale), dtype=_HALF))
-        check(lib.qs_invoke_quant_scalar(out.data_ptr(), input.data_ptr(), s, tokens, hidden, _stream(input)))
+        _call(input, lib.qs_invoke_quant_scalar, out.data_ptr(), input.data_ptr(), s, tokens, hidden)
 
 
 def invoke_quant_fuse_sum(out, input, input_sum, scale) -> None:
@@ -284,10 +298,10 @@ def invoke_quant_fuse_sum(out, input, input_sum, scale) -> None:
         return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
-        check(lib.qs_invoke_quant_fuse_sum(out.data_ptr(), input.data_ptr(), input_sum.data_ptr(), scale.data_ptr(), tokens, hidden, _stream(input)))
+        _call(input, lib.qs_invoke_quant_fuse_sum, out.data_ptr(), input.data_ptr(), input_sum.data_ptr(), scale.data_ptr(), tokens, hidden)
     else:  # scalar overload: static scale, the sum argument is unused by the reference kernel (fused_kernels.cu:131-136)
         s = float(torch.tensor(float(scale), dtype=_HALF))
-        check(lib.qs_invoke_quant_scalar(out.data_ptr(), input.data_ptr(), s, tokens, hidden, _stream(input)))
+        _call(input, lib.qs_invoke_quant_scalar, out.data_ptr(), input.data_ptr(), s, tokens, hidden)
 
 
 def invoke_dequant_add_residual(out, input, residual, scale) -> None:
@@ -297,10 +311,10 @@ def invoke_dequant_add_residual(out, input, residual, scale) -> None:
         return
     tokens, hidden = _rows(input)
     if isinstance(scale, torch.Tensor):
-        check(lib.qs_invoke_dequant_add_residual(out.data_ptr(), input.data_ptr(), residual.data_ptr(), scale.data_ptr(), 0.0, tokens, hidden, _stream(input)))
+        _call(input, lib.qs_invoke_dequant_add_residual, out.data_ptr(), input.data_ptr(), residual.data_ptr(), scale.data_ptr(), 0.0, tokens, hidden)
     else:
         s = float(torch.tensor(float(scale), dtype=_HALF))
-        check(lib.qs_invoke_dequant_add_residual(out.data_ptr(), input.data_ptr(), residual.data_ptr(), None, s, tokens, hidden, _stream(input)))
+        _call(input, lib.qs_invoke_dequant_add_residual, out.data_ptr(), input.data_ptr(), residual.data_ptr(), None, s, tokens, hidden)
 
 
 def invoke_dequant(out, input, scale) -> None:
@@ -310,7 +324,7 @@ def invoke_dequant(out, input, scale) -> None:
         return
     tokens, hidden = _rows(input)
     s = float(torch.tensor(float(scale), dtype=_HALF))
-    check(lib.qs_invoke_dequant(out.data_ptr(), input.data_ptr(), s, tokens, hidden, input.stride(-2), out.stride(-2), _stream(input)))
+    _call(input, lib.qs_invoke_dequant, out.data_ptr(), input.data_ptr(), s, tokens, hidden, input.stride(-2), out.stride(-2))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -325,21 +339,21 @@ def silu_and_mul(out, input) -> None:
         return
     d = input.size(-1) // 2
     tokens = input.numel() // input.size(-1) if input.size(-1) else 0
-    check(lib.qs_silu_and_mul(out.data_ptr(), input.data_ptr(), tokens, d, _stream(input)))
+    _call(input, lib.qs_silu_and_mul, out.data_ptr(), input.data_ptr(), tokens, d)
 
 
 def gelu_new(out, input) -> None:
     """activation_ops.gelu_new (activation.cpp:27)."""
     _cuda(input, "input"); _half_only(input, "gelu_new")
     tokens, d = _rows(input)
-    check(lib.qs_gelu_new(out.data_ptr(), input.data_ptr(), tokens, d, _stream(input)))
+    _call(input, lib.qs_gelu_new, out.data_ptr(), input.data_ptr(), tokens, d)
 
 
 def gelu_fast(out, input) -> None:
     """activation_ops.gelu_fast (activation.cpp:28)."""
     _cuda(input, "input"); _half_only(input, "gelu_fast")
     tokens, d = _rows(input)
-    check(lib.qs_gelu_fast(out.data_ptr(), input.data_ptr(), tokens, d, _stream(input)))
+    _call(input, lib.qs_gelu_fast, out.data_ptr(), input.data_ptr(), tokens, d)
 
 
 def invoke_dequant_silu_and_mul_quant(out, input, scale_gate: float, scale_up: float, scale_out, tmp: Optional[torch.Tensor] = None) -> None:
@@ -349,11 +363,11 @@ def invoke_dequant_silu_and_mul_quant(out, input, scale_gate: float, scale_up: f
     tokens = input.numel() // input.size(-1) if input.size(-1) else 0
     if isinstance(scale_out, torch.Tensor):
         _require(tmp is not None, "per-token overload needs the tmp buffer")
-        check(lib.qs_dequant_silu_and_mul_quant(out.data_ptr(), input.data_ptr(), float(scale_gate), float(scale_up), 0.0, scale_out.data_ptr(),
-                                                tmp.data_ptr(), tokens, d, _stream(input)))
+        _call(input, lib.qs_dequant_silu_and_mul_quant, out.data_ptr(), input.data_ptr(), float(scale_gate), float(scale_up), 0.0, scale_out.data_ptr(),
+                                                tmp.data_ptr(), tokens, d)
     else:
-        check(lib.qs_dequant_silu_and_mul_quant(out.data_ptr(), input.data_ptr(), float(scale_gate), float(scale_up), float(scale_out), None, None,
-                                                tokens, d, _stream(input)))
+        _call(input, lib.qs_dequant_silu_and_mul_quant, out.data_ptr(), input.data_ptr(), float(scale_gate), float(scale_up), float(scale_out), None, None,
+                                                tokens, d)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -367,9 +381,8 @@ def add_rms_norm_general(out, hidden_out, x, delta, weight, input_sum: Optional[
     if _noop(x):
         return
     tokens, hidden = _rows(x)
-    check(lib.qs_add_rms_norm_general(out.data_ptr(), hidden_out.data_ptr(), x.data_ptr(), delta.data_ptr(), weight.data_ptr(),
-                                      input_sum.data_ptr() if input_sum is not None else None, scaling.data_ptr(), float(epsilon), tokens, hidden,
-                                      _stream(x)))
+    _call(x, lib.qs_add_rms_norm_general, out.data_ptr(), hidden_out.data_ptr(), x.data_ptr(), delta.data_ptr(), weight.data_ptr(),
+                                      input_sum.data_ptr() if input_sum is not None else None, scaling.data_ptr(), float(epsilon), tokens, hidden)
 
 
 def silu_and_mul_quant(out, input, input_sum: Optional[torch.Tensor], scale) -> None:
@@ -379,8 +392,8 @@ def silu_and_mul_quant(out, input, input_sum: Optional[torch.Tensor], scale) -> 
         return
     d = input.size(-1) // 2
     tokens = input.numel() // input.size(-1)
-    check(lib.qs_silu_and_mul_quant(out.data_ptr(), input.data_ptr(), input_sum.data_ptr() if input_sum is not None else None, scale.data_ptr(),
-                                    tokens, d, _stream(input)))
+    _call(input, lib.qs_silu_and_mul_quant, out.data_ptr(), input.data_ptr(), input_sum.data_ptr() if input_sum is not None else None, scale.data_ptr(),
+                                    tokens, d)
 
 
 def single_query_attention_quant(q, k, v, kv_pointers, length_per_sample, memory_max_seqlen: int, tokens_per_block: int, size_per_token: int,
@@ -396,12 +409,33 @@ def single_query_attention_quant(q, k, v, kv_pointers, length_per_sample, memory
     _require(k.stride(1) == headdim and v.stride(1) == headdim and kv_pointers.is_contiguous(), "k, v, kv_pointers layout")
     _require(out_q.dtype == torch.int8 and out_q.is_contiguous() and out_q.numel() == batch * nheads * headdim, "out_q must be int8 [B, Hq*D]")
     ws = attention_workspace(q.device, batch, nheads, headdim)
-    check(lib.qs_single_query_attention_quant(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0), kv_pointers.data_ptr(),
+    _call(q, lib.qs_single_query_attention_quant, q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0), kv_pointers.data_ptr(),
                                               length_per_sample.data_ptr(), out_q.data_ptr(), out_scale.data_ptr(),
                                               out_sum.data_ptr() if out_sum is not None else None, batch, nheads, nheads_kv, headdim,
                                               kv_pointers.size(-1), int(memory_max_seqlen), int(tokens_per_block), int(size_per_token), int(timestep),
                                               int(rotary_embedding_dim), float(rotary_base), int(bool(int4_kv_cache)), int(bool(kv_cache_with_zeros)),
-                                              ws.data_ptr(), ws.numel(), _stream(q)))
+                                              ws.data_ptr(), ws.numel())
+
+
+def row_absmax(amax_out: torch.Tensor, input: torch.Tensor) -> None:
+    """Tensor-parallel extension: amax_out[t] (fp32) = max |input[t, :]| of this rank's shard (then max-all-reduced by the caller)."""
+    _cuda(input, "input"); _half_only(input, "row_absmax")
+    _require(input.is_contiguous() and amax_out.dtype == torch.float32, "row_absmax: contiguous fp16 input, fp32 output")
+    if _noop(input):
+        return
+    tokens, hidden = _rows(input)
+    _call(input, lib.qs_row_absmax, amax_out.data_ptr(), input.data_ptr(), tokens, hidden)
+
+
+def invoke_quant_given_amax(out, input, amax: torch.Tensor, input_sum: Optional[torch.Tensor], scale) -> None:
+    """Tensor-parallel extension: invoke_quant[_fuse_sum] with a caller-supplied (global) per-token amax, fp32 [tokens]."""
+    _cuda(input, "input"); _half_only(input, "invoke_quant_given_amax")
+    _require(input.is_contiguous() and out.is_contiguous() and amax.dtype == torch.float32, "invoke_quant_given_amax: contiguous tensors, fp32 amax")
+    if _noop(input):
+        return
+    tokens, hidden = _rows(input)
+    _call(input, lib.qs_invoke_quant_given_amax, out.data_ptr(), input.data_ptr(), amax.data_ptr(), input_sum.data_ptr() if input_sum is not None else None,
+          scale.data_ptr(), tokens, hidden)
 
 
 def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -412,5 +446,5 @@ def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> tor
         out = torch.empty(logits.size(0), dtype=torch.int64, device=logits.device)
     if logits.size(0) == 0:
         return out
-    check(lib.qs_argmax_rows(out.data_ptr(), logits.data_ptr(), logits.size(0), logits.size(1), _stream(logits)))
+    _call(logits, lib.qs_argmax_rows, out.data_ptr(), logits.data_ptr(), logits.size(0), logits.size(1))
     return out

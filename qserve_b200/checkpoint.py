@@ -168,10 +168,17 @@ def _cat(parts, suffix: str) -> torch.Tensor:
     return torch.cat(parts, dim=1 if suffix in ("s2_scales", "s2_zeros") else 0).contiguous()
 
 
-def fuse_llama_state_dict(sd: Dict[str, torch.Tensor], num_layers: int, tp_rank: int = 0, tp_size: int = 1) -> Dict[str, torch.Tensor]:
+def fuse_llama_state_dict(sd: Dict[str, torch.Tensor], num_layers: int, tp_rank: int = 0, tp_size: int = 1, w_bit: int = 4) -> Dict[str, torch.Tensor]:
     """Per-projection checkpoint tensors -> the fused, per-rank buffers the model owns: `qkv_proj` = q | k | v and
     `gate_up_proj` = gate | up along the output channels (column parallel: every part is sliced first, then concatenated),
-    `o_proj` / `down_proj` sliced along K (row parallel; per-channel vectors are replicated)."""
+    `o_proj` / `down_proj` sliced along K (row parallel; per-channel vectors are replicated).
+
+    `w_bit == 4` reproduces the W4A8 loader's `if "norm" in name: continue` (llama_w4a8_unpad.py:541-542): every norm tensor of the
+    checkpoint (input_layernorm, post_attention_layernorm AND the final model.norm) is dropped and gamma stays 1, because LMQuant has
+    folded it into the following linear layer.  Only the W8A8 loader (`w_bit == 8`, llama_w8a8_unpad.py) loads them."""
+    if w_bit not in (4, 8):
+        raise ValueError(f"w_bit must be 4 or 8, got {w_bit}")
+    load_norms = (w_bit == 8)
     out: Dict[str, torch.Tensor] = {}
     suffixes = sorted({k.rsplit(".", 1)[1] for k in sd if "_proj." in k})
     for i in range(num_layers):
@@ -195,17 +202,19 @@ def fuse_llama_state_dict(sd: Dict[str, torch.Tensor], num_layers: int, tp_rank:
                     t = _ROW[suf](t, tp_rank, tp_size)
                 out[key] = t.contiguous()
         for k in (f"{pre}input_layernorm.weight", f"{pre}post_attention_layernorm.weight"):
-            if k in sd:
+            if k in sd and load_norms:
                 out[k] = sd[k]
     for k in ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight"):
-        if k in sd:
+        if k in sd and (load_norms or "norm" not in k):
             out[k] = sd[k]
     return out
 
 
 def load_into_runner(runner, fused: Dict[str, torch.Tensor]) -> int:
     """Install a fused (per-rank) state dict into a DecodeRunner built for the same model / precision.  Returns the number of
-    tensors installed; shape or dtype mismatches raise."""
+    tensors installed; shape or dtype mismatches raise.  A W4A8 runner never takes norm tensors (gamma = 1, see
+    fuse_llama_state_dict), even if the dict still carries them."""
+    take_norms = runner.wmode == "w8"
     names = {"qkv": "self_attn.qkv_proj", "o": "self_attn.o_proj", "gate_up": "mlp.gate_up_proj", "down": "mlp.down_proj"}
     attr = {"qweight": "qweight", "s1_scales": "s1", "s1_szeros": "s1z", "s2_scales": "s2_scales", "s2_zeros": "s2_zeros",
             "weight": "weight", "dequant_scale": "wscale"}
@@ -226,9 +235,9 @@ def load_into_runner(runner, fused: Dict[str, torch.Tensor]) -> int:
                 if key in fused and hasattr(lin, a):
                     put(getattr(lin, a), fused[key], key)
         for key, slot in ((f"model.layers.{i}.input_layernorm.weight", "ln1"), (f"model.layers.{i}.post_attention_layernorm.weight", "ln2")):
-            if key in fused:
+            if key in fused and take_norms:
                 put(ly[slot], fused[key], key)
     for key, t in (("model.embed_tokens.weight", runner.embed), ("model.norm.weight", runner.norm_w), ("lm_head.weight", runner.lm_head)):
-        if key in fused:
+        if key in fused and (take_norms or "norm" not in key):
             put(t, fused[key], key)
     return n

@@ -167,7 +167,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
   // The sequence lengths and the page-pointer table are prepared by the host side before the step (model_runner.py:506-530):
   // they are read BEFORE the dependency wait, so that the chain length -> page pointers -> first bulk copy (two dependent
   // global round trips) overlaps the tail of the preceding qkv GEMM.  Page CONTENTS and q/k/v are only touched after the wait.
-  const int tlen = (lengths ? lengths[b] : timestep) - 1;  // tokens already in the cache (Template.hpp:901)
+  const int tlen = lengths ? lengths[b] - 1 : timestep;  // tokens already in the cache (Template.hpp:901: length_per_sample ? len - 1 : timestep)
   const long long* kptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 0) * max_blocks;
   const long long* vptrs = kv_pointers + (static_cast<size_t>(b) * 2 + 1) * max_blocks;
   const int n_pages = (tlen + kPageTokens - 1) / kPageTokens;
@@ -902,12 +902,12 @@ int decode_attention(const DecodeAttnArgs& a) {
   }
   dim3 grid(gx, a.batch, nsplit);
   auto run = [&](auto kern, size_t smem) {
-    static bool attr_done[2] = {false, false};
-    const int which = a.int4_kv ? 0 : 1;
-    if (!attr_done[which]) {
+    static bool attr_done[2][kMaxDevices] = {};
+    bool& done = attr_done[a.int4_kv ? 0 : 1][device_ordinal()];
+    if (!done) {
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)), "attention smem attribute");
       if (rc) return rc;
-      attr_done[which] = true;
+      done = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;

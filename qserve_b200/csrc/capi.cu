@@ -30,6 +30,22 @@ int check_cuda(cudaError_t e, const char* what) {
 
 bool pdl_enabled() { return g_pdl != 0; }
 
+int device_ordinal() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+int num_sms() {
+  static int sms[kMaxDevices] = {};
+  const int dev = device_ordinal();
+  if (!sms[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
+  }
+  return sms[dev];
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace qs
@@ -197,6 +213,16 @@ int qs_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_sum, vo
   QS_REQUIRE(out && input && scale && input_sum, "invoke_quant_fuse_sum: null tensor");
   QS_REQUIRE(aligned16(out) && aligned16(input), "invoke_quant_fuse_sum: tensors must be 16-byte aligned");
   return quant_per_token(out, input, input_sum, scale, tokens, hidden, stream);
+}
+int qs_row_absmax(float* amax_out, const void* input, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(amax_out && input, "row_absmax: null tensor");
+  QS_REQUIRE(aligned16(input), "row_absmax: input must be 16-byte aligned");
+  return row_absmax(amax_out, input, tokens, hidden, stream);
+}
+int qs_invoke_quant_given_amax(int8_t* out, const void* input, const float* amax, void* input_sum, void* scale, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && input && amax && scale, "invoke_quant_given_amax: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(input), "invoke_quant_given_amax: tensors must be 16-byte aligned");
+  return quant_given_amax(out, input, amax, input_sum, scale, tokens, hidden, stream);
 }
 int qs_invoke_dequant_add_residual(void* out, const int32_t* input, const void* residual, const void* scale_vec, float scale, int tokens,
                                    int hidden, void* stream) {

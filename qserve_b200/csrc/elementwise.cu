@@ -424,6 +424,59 @@ __global__ void __launch_bounds__(kThreads) quant_per_token_kernel(int8_t* __res
   }
 }
 
+// Tensor-parallel parity rule: a row-parallel GEMM keeps INT32 partial sums that add up to the single-GPU
+// accumulators only if every rank quantises its K shard of a token with the SAME per-token scale.  row_absmax -> [M] fp32
+// max-allreduce -> quant_given_amax does exactly the arithmetic of quant_per_token_kernel with the global amax; the row sum
+// (per-channel W4A8 zero-point term) stays the LOCAL shard's sum.
+__global__ void __launch_bounds__(kThreads) row_absmax_kernel(float* __restrict__ amax_out, const __half* __restrict__ in, int H) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * H);
+  float amax = 0.f;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = src[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  amax = block_reduce(amax, red, OpMax(), 0.f);
+  if (threadIdx.x == 0) amax_out[row] = amax;
+}
+
+__global__ void __launch_bounds__(kThreads) quant_given_amax_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
+                                                                   const float* __restrict__ amax_in, __half* __restrict__ input_sum,
+                                                                   __half* __restrict__ scale, int H) {
+  __shared__ long long red_ll[32];
+  const int row = blockIdx.x;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  const float amax = amax_in[row];
+  const float qs_ = __fdiv_rn(127.f, amax);
+  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * H);
+  long long s = 0;
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = src[i];
+    const __half* h = reinterpret_cast<const __half*>(&v);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[j] = __half2float(h[j]);
+      if (input_sum) s += fx_of_half(x[j]);
+    }
+    store_q8(out + static_cast<size_t>(row) * H, i, x, qs_);
+  }
+  if (input_sum) {
+    const long long total = block_sum_ll(s, red_ll);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(fx_to_float(total));
+  }
+  if (threadIdx.x == 0) scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+}
+
 __global__ void quant_scalar_kernel(int8_t* __restrict__ out, const __half* __restrict__ in, float scale, size_t n) {
   if (threadIdx.x == 0) pdl_launch_dependents();
   pdl_wait();
@@ -725,6 +778,19 @@ int quant_per_token(void* out_q, const void* in, void* input_sum, void* scale, i
   if (rc) return rc;
   return launch(quant_per_token_kernel, dim3(tokens), dim3(kThreads), smem, stream, "invoke_quant", static_cast<int8_t*>(out_q),
                 static_cast<const __half*>(in), static_cast<__half*>(input_sum), static_cast<__half*>(scale), hidden);
+}
+
+int row_absmax(void* amax_f32, const void* in, int tokens, int hidden, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "row_absmax: hidden=%d must be a positive multiple of 8", hidden);
+  return launch(row_absmax_kernel, dim3(tokens), dim3(kThreads), 0, stream, "row_absmax", static_cast<float*>(amax_f32), static_cast<const __half*>(in), hidden);
+}
+
+int quant_given_amax(void* out_q, const void* in, const void* amax_f32, void* input_sum, void* scale, int tokens, int hidden, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "quant_given_amax: hidden=%d must be a positive multiple of 8", hidden);
+  return launch(quant_given_amax_kernel, dim3(tokens), dim3(kThreads), 0, stream, "quant_given_amax", static_cast<int8_t*>(out_q),
+                static_cast<const __half*>(in), static_cast<const float*>(amax_f32), static_cast<__half*>(input_sum), static_cast<__half*>(scale), hidden);
 }
 
 int quant_scalar(void* out_q, const void* in, float scale, int tokens, int hidden, void* stream) {

@@ -827,17 +827,6 @@ int make_tmap_w4(CUtensorMap* m, const void* ptr, uint64_t N, uint64_t K, uint32
   return QS_OK;
 }
 
-int g_num_sms = 0;
-int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
 int choose_split(int tiles, int kb_per_tile, int forced) {
   int s = 1;
   if (forced > 0) {
@@ -881,12 +870,13 @@ int launch_gemm(const GemmArgs& a) {
   if (rc) return rc;
 
   auto kern = a.acc_out ? gemm_kernel<MODE, NT, WS, AS, true> : gemm_kernel<MODE, NT, WS, AS, false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[a.acc_out ? 1 : 0]) {
+  static bool attr_set[2][kMaxDevices] = {};  // per (instantiation, device): the attribute is a per-device property of the function
+  bool& done = attr_set[a.acc_out ? 1 : 0][device_ordinal()];
+  if (!done) {
     rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSplitFits ? C::kSmemBytesSplit : C::kSmemBytes),
                     "cudaFuncSetAttribute(gemm smem)");
     if (rc) return rc;
-    attr_set[a.acc_out ? 1 : 0] = true;
+    done = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles * p.split);
@@ -933,11 +923,12 @@ int launch_gemm_wide(const GemmArgs& a) {
   rc = make_tmap_w4(&tm_hi, a.weight, a.N, a.K, nb_lo + (bands % grid ? 1 : 0));
   if (rc) return rc;
   auto kern = a.acc_out ? gemm_wide_kernel<NT, WS, AS, true> : gemm_wide_kernel<NT, WS, AS, false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[a.acc_out ? 1 : 0]) {
+  static bool attr_set[2][kMaxDevices] = {};
+  bool& done = attr_set[a.acc_out ? 1 : 0][device_ordinal()];
+  if (!done) {
     rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "cudaFuncSetAttribute(gemm wide smem)");
     if (rc) return rc;
-    attr_set[a.acc_out ? 1 : 0] = true;
+    done = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);

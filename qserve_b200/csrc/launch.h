@@ -6,6 +6,10 @@
 namespace qs {
 
 bool pdl_enabled();
+// host-side caches (kernel attributes, SM count) are keyed by the CURRENT device ordinal: one process may drive several GPUs
+constexpr int kMaxDevices = 64;
+int device_ordinal();
+int num_sms();
 
 struct GemmArgs {
   const void* act = nullptr;        // int8 [M, K]
@@ -41,6 +45,8 @@ int layernorm_general_quant(void* out_q, const void* in, const void* gamma, void
                             int hidden, int per_token, void* stream);
 int quant_per_token(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int hidden, void* stream);
 int quant_scalar(void* out_q, const void* in, float scale, int tokens, int hidden, void* stream);
+int row_absmax(void* amax_f32, const void* in, int tokens, int hidden, void* stream);
+int quant_given_amax(void* out_q, const void* in, const void* amax_f32, void* input_sum, void* scale, int tokens, int hidden, void* stream);
 int silu_and_mul(void* out, const void* in, int tokens, int d, void* stream);
 int argmax_rows(void* out_i64, const void* logits_f16, int rows, int vocab, void* stream);
 int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int d, void* stream);

@@ -116,7 +116,33 @@ def test_convert_and_fuse_tensor_parallel_shards_reassemble(group):
         assert torch.equal(full[pre + "mlp.gate_up_proj.s2_scales"][:, :I], sd[pre + "mlp.gate_proj.s2_scales"])
     else:
         assert torch.equal(full[pre + "mlp.gate_up_proj.s1_szeros"][I:], sd[pre + "mlp.up_proj.s1_szeros"])
-    assert pre + "input_layernorm.weight" in full and "lm_head.weight" in full
+    # the W4A8 loader drops every norm tensor (llama_w4a8_unpad.py:541-542); everything else passes through
+    assert pre + "input_layernorm.weight" not in full and "model.norm.weight" not in full and "lm_head.weight" in full
+
+
+def test_w4a8_loader_skips_norm_tensors_w8a8_loads_them():
+    """a W4A8 checkpoint with NON-unit norm tensors must not get gamma applied twice -- the reference's W4A8 loader
+    skips every tensor whose name contains 'norm' (gamma stays 1, LMQuant folded it into the next linear); the W8A8 loader keeps them."""
+    H = 128
+    sd = {"model.layers.0.input_layernorm.weight": torch.full((H,), 3.0), "model.layers.0.post_attention_layernorm.weight": torch.full((H,), 5.0),
+          "model.norm.weight": torch.full((H,), 7.0), "model.embed_tokens.weight": torch.zeros(4, H), "lm_head.weight": torch.zeros(4, H)}
+    w4 = ck.fuse_llama_state_dict(sd, 1, w_bit=4)
+    assert not any("norm" in k for k in w4) and "lm_head.weight" in w4 and "model.embed_tokens.weight" in w4
+    w8 = ck.fuse_llama_state_dict(sd, 1, w_bit=8)
+    assert float(w8["model.layers.0.input_layernorm.weight"][0]) == 3.0 and float(w8["model.norm.weight"][0]) == 7.0
+
+    class _Runner:  # load_into_runner only touches these attributes
+        def __init__(self, wmode):
+            self.wmode = wmode
+            self.layers = [{"ln1": torch.ones(H), "ln2": torch.ones(H)}]
+            self.embed, self.norm_w, self.lm_head = torch.ones(4, H), torch.ones(H), torch.ones(4, H)
+    r4, r8 = _Runner("chn"), _Runner("w8")
+    for k in ("qkv", "o", "gate_up", "down"):
+        r4.layers[0][k] = object(); r8.layers[0][k] = object()
+    ck.load_into_runner(r4, sd)   # even a dict that still carries the norms leaves a W4A8 runner at gamma = 1
+    assert float(r4.layers[0]["ln1"][0]) == 1.0 and float(r4.layers[0]["ln2"][0]) == 1.0 and float(r4.norm_w[0]) == 1.0
+    ck.load_into_runner(r8, w8)
+    assert float(r8.layers[0]["ln1"][0]) == 3.0 and float(r8.layers[0]["ln2"][0]) == 5.0 and float(r8.norm_w[0]) == 7.0
 
 
 def test_convert_rejects_inconsistent_group_metadata():

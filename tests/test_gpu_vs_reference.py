@@ -1,0 +1,309 @@
+"""DIRECT comparison of this repo's CUDA kernels with the reference's kernels (VERDICT r1 "What's weak": the r1 chain was only
+CUDA == oracle and oracle ~ reference).
+
+Part 1 (always runs on the GPU box): the committed golden vectors `tests/golden/ref_*.npz` hold inputs AND outputs of the
+UNMODIFIED reference CUDA kernels run on a B200; our kernels are fed the same inputs through the C ABI and must reproduce the
+outputs within the bars of tests/test_oracle_vs_reference_golden.py (the reference is built with --use_fast_math: approximate
+division / sin / cos and FMA contraction move a result by at most one rounding step).
+
+Part 2 (runs when oracle/_ref/*.so are present: they are built from /root/reference by oracle/build_ref.py and travel to the
+GPU box): the reference extensions are loaded LIVE next to ours and both run on the same seeded inputs at the BASELINE config
+shapes (config 2: Llama-3-8B M=64 per-channel; config 3: g128; config 4: W8A8 M=128; config-2 attention B=64 ctx=1024).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import bits16, np_of, to_dev, ulp16_diff
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gold(name):
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} missing")
+    return np.load(path)
+
+
+def _qb():
+    import qserve_backend as qb
+
+    return qb
+
+
+# =====================================================================================================================
+# Part 1: golden inputs / outputs of the reference kernels
+# =====================================================================================================================
+def test_golden_gemms(dev):
+    qb = _qb()
+    g = _gold("ref_gemm_per_chn.npz")
+    out = torch.empty(g["out"].shape, dtype=torch.half, device=dev)
+    qb.qgemm_w4a8_per_chn.gemm_forward_cuda(to_dev(g["aq"], dev), to_dev(g["qw"], dev), to_dev(g["s1"], dev), to_dev(g["sa"], dev),
+                                            to_dev(g["s1z"], dev), to_dev(g["asum"], dev), out)
+    d = ulp16_diff(np_of(out), g["out"])
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    g = _gold("ref_gemm_per_group.npz")
+    out = torch.empty(g["out"].shape, dtype=torch.half, device=dev)
+    qb.qgemm_w4a8_per_group.gemm_forward_cuda(to_dev(g["aq"], dev), to_dev(g["qw"], dev), to_dev(g["s2z"], dev), to_dev(g["s2s"], dev),
+                                              to_dev(g["s1"], dev), to_dev(g["sa"], dev), out)
+    d = ulp16_diff(np_of(out), g["out"])
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    g = _gold("ref_gemm_w8a8.npz")
+    out = torch.empty(g["out"].shape, dtype=torch.half, device=dev)
+    qb.qgemm_w8a8.w8a8_gemm_forward_cuda(to_dev(g["aq"], dev), to_dev(g["w"], dev), to_dev(g["sw"], dev), to_dev(g["sa"], dev), out)
+    d = ulp16_diff(np_of(out), g["out"])
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+def test_golden_elementwise(dev):
+    qb = _qb()
+    g = _gold("ref_elementwise.npz")
+    x, gamma = to_dev(g["x"], dev), to_dev(g["gamma"], dev)
+    M, H = g["x"].shape
+    q = torch.empty((M, H), dtype=torch.int8, device=dev); s = torch.empty(M, dtype=torch.half, device=dev); sm = torch.empty(M, dtype=torch.half, device=dev)
+    qb.fused_kernels.invoke_quant_fuse_sum(q, x, sm, s)
+    dq = np.abs(np_of(q).astype(np.int32) - g["quant_q"].astype(np.int32))
+    assert dq.max() <= 1 and (dq > 0).mean() < 5e-4
+    assert np.array_equal(bits16(np_of(s)), bits16(g["quant_scale"])) and np.array_equal(bits16(np_of(sm)), bits16(g["quant_sum"]))
+    qb.layernorm_ops.rms_norm_general_fuse_sum(q, x, gamma, sm, s, 1e-5, True)
+    dq = np.abs(np_of(q).astype(np.int32) - g["ln_q"].astype(np.int32))
+    assert dq.max() <= 1 and (dq > 0).mean() < 2e-3          # fp32 row statistics are reduction-order dependent
+    assert ulp16_diff(np_of(s), g["ln_scale"]).max() <= 1 and ulp16_diff(np_of(sm), g["ln_sum"]).max() <= 2
+    o = torch.empty((M, H), dtype=torch.half, device=dev)
+    qb.layernorm_ops.rms_norm(o, x, gamma, 1e-5, False)
+    assert ulp16_diff(np_of(o), g["rms"]).max() <= 1
+    o2 = torch.empty((M, H // 2), dtype=torch.half, device=dev)
+    qb.activation_ops.silu_and_mul(o2, x)
+    d = ulp16_diff(np_of(o2), g["silu"])
+    assert d.max() <= 2 and (d > 0).mean() < 2e-3
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_golden_decode_attention(dev, bits):
+    qb = _qb()
+    g = _gold(f"ref_decode_attn_kv{bits}.npz")
+    B, Hq, D = g["q"].shape
+    Hkv = g["k"].shape[1]
+    kd, vd = to_dev(g["kpool"], dev), to_dev(g["vpool"], dev)
+    pb = g["kpool"].shape[1]
+    table = torch.from_numpy(np.stack([kd.data_ptr() + g["bt"].astype(np.int64) * pb, vd.data_ptr() + g["bt"].astype(np.int64) * pb], axis=1)).to(dev)
+    qkv = torch.from_numpy(np.concatenate([g["q"].reshape(B, -1), g["k"].reshape(B, -1), g["v"].reshape(B, -1)], axis=1)).to(dev)
+    q, k, v = qkv.split([Hq * D, Hkv * D, Hkv * D], dim=-1)
+    lens = [int(x) for x in g["lens"]]
+    o = qb.fused_attention.single_query_attention(q.reshape(B, Hq, D), k.reshape(B, Hkv, D), v.reshape(B, Hkv, D), table,
+                                                  torch.tensor(lens, dtype=torch.int32, device=dev), None, 8192, 64, Hkv * D * bits // 8, max(lens), D,
+                                                  10000.0, True, bits == 4, True)
+    torch.cuda.synchronize()
+    ref = g["out"].astype(np.float32)
+    assert np.abs(np_of(o).astype(np.float32) - ref).max() <= 1e-2 * max(1.0, np.abs(ref).max())
+    assert (np_of(vd) != g["vpool_after"]).mean() < 1e-4   # V append: pure IEEE on both sides
+    assert (np_of(kd) != g["kpool_after"]).mean() < 1e-3   # K goes through fast-math RoPE in the reference
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_golden_prefill_append(dev, bits):
+    qb = _qb()
+    g = _gold(f"ref_prefill_kv{bits}.npz")
+    Hq, Hkv, D = 8, 2, 128
+    lens = g["lens"].astype(np.int32)
+    T, maxlen = int(lens.sum()), int(lens.max())
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    pad = qb.fused_attention.compute_padding_offsets(to_dev(cu, dev), maxlen, T)
+    assert np.array_equal(np_of(pad), g["pad"])
+    npages, pb = g["kpool_after"].shape
+    kd = torch.zeros((npages, pb), dtype=torch.uint8, device=dev); vd = torch.zeros((npages, pb), dtype=torch.uint8, device=dev)
+    bt = g["bt"].astype(np.int64)
+    table = torch.from_numpy(np.stack([kd.data_ptr() + bt * pb, vd.data_ptr() + bt * pb], axis=1)).to(dev)
+    qkv = to_dev(g["qkv"], dev)
+    qb.fused_attention.apply_bias_rope_update_kv_cache(qkv, to_dev(lens, dev), pad, table, Hq, Hkv, maxlen, 64, Hkv * D * bits // 8, D, 10000.0, 8192,
+                                                       True, bits == 4, True)
+    torch.cuda.synchronize()
+    assert np.abs(np_of(qkv).astype(np.float32) - g["qkv_after"].astype(np.float32)).max() <= 4e-3
+    cb = 64 * Hkv * D * bits // 8
+    for mine, ref in ((np_of(kd), g["kpool_after"]), (np_of(vd), g["vpool_after"])):  # both pools start zeroed
+        assert (mine != ref).mean() < 1e-3
+        if bits == 8:
+            assert np.abs(mine[:, :cb].astype(np.int32) - ref[:, :cb].astype(np.int32)).max() <= 1
+
+
+# =====================================================================================================================
+# Part 2: the reference extensions, live, at the BASELINE config shapes
+# =====================================================================================================================
+def _ref(name):
+    from tests import refmods
+
+    m = refmods.load(name)
+    if m is None:
+        pytest.skip(f"oracle/_ref/ref_{name}.so not built (oracle/build_ref.py needs /root/reference)")
+    return m
+
+
+def _act(rng, M, K, dev):
+    x = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float16)).to(dev)
+    q = torch.empty((M, K), dtype=torch.int8, device=dev); s = torch.empty(M, dtype=torch.half, device=dev); sm = torch.empty(M, dtype=torch.half, device=dev)
+    _qb().fused_kernels.invoke_quant_fuse_sum(q, x, sm, s)
+    return q, s, sm
+
+
+LLAMA_SHAPES = [(4096, 6144), (4096, 4096), (4096, 28672), (14336, 4096)]  # (K, N) of qkv / o / gate_up / down
+
+
+@pytest.mark.parametrize("K,N", LLAMA_SHAPES)
+def test_live_gemm_per_channel_config2(dev, K, N):
+    ref, qb = _ref("qgemm_w4a8_per_chn"), _qb()
+    rng = np.random.default_rng(K + N)
+    M = 64
+    aq, sa, asum = _act(rng, M, K, dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    qw = torch.randint(-128, 128, (N, K // 2), dtype=torch.int8, device=dev, generator=g)
+    s1 = (torch.rand(N, device=dev, generator=g) * 0.015 + 0.005).half()
+    s1z = (torch.randint(0, 16, (N,), device=dev, generator=g).float() * s1.float()).half()
+    o_ref = torch.zeros((M, N), dtype=torch.half, device=dev); o = torch.empty_like(o_ref)
+    ref.gemm_forward_cuda(aq, qw, s1, sa, s1z, asum, o_ref)
+    qb.qgemm_w4a8_per_chn.gemm_forward_cuda(aq, qw, s1, sa, s1z, asum, o)
+    torch.cuda.synchronize()
+    d = ulp16_diff(np_of(o), np_of(o_ref))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
+
+
+@pytest.mark.parametrize("K,N", LLAMA_SHAPES)
+@pytest.mark.parametrize("M", [64, 512])
+def test_live_gemm_per_group_config3(dev, K, N, M):
+    ref, qb = _ref("qgemm_w4a8_per_group"), _qb()
+    rng = np.random.default_rng(K + N + M)
+    aq, sa, _ = _act(rng, M, K, dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    qw = torch.randint(-128, 128, (N, K // 2), dtype=torch.int8, device=dev, generator=g)
+    s2 = torch.randint(1, 17, (K // 128, N), dtype=torch.int8, device=dev, generator=g)
+    z = torch.randint(0, 16, (K // 128, N), dtype=torch.int8, device=dev, generator=g)
+    s2z = (-(z.int()) * s2.int()).to(torch.int8)
+    s1 = (torch.rand(N, device=dev, generator=g) * 0.003 + 0.001).half()
+    o_ref = torch.zeros((M, N), dtype=torch.half, device=dev); o = torch.empty_like(o_ref)
+    ref.gemm_forward_cuda(aq, qw, s2z, s2, s1, sa, o_ref)
+    qb.qgemm_w4a8_per_group.gemm_forward_cuda(aq, qw, s2z, s2, s1, sa, o)
+    torch.cuda.synchronize()
+    d = ulp16_diff(np_of(o), np_of(o_ref))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
+
+
+@pytest.mark.parametrize("K,N", LLAMA_SHAPES)
+def test_live_gemm_w8a8_config4(dev, K, N):
+    ref, qb = _ref("qgemm_w8a8"), _qb()
+    rng = np.random.default_rng(K + N)
+    M = 128
+    aq, sa, _ = _act(rng, M, K, dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    w = torch.randint(-127, 128, (N, K), dtype=torch.int8, device=dev, generator=g)
+    sw = (torch.rand(N, device=dev, generator=g) * 0.0003 + 0.0001).half()
+    o_ref = torch.zeros((M, N), dtype=torch.half, device=dev); o = torch.empty_like(o_ref)
+    ref.w8a8_gemm_forward_cuda(aq, w, sw, sa, o_ref)
+    qb.qgemm_w8a8.w8a8_gemm_forward_cuda(aq, w, sw, sa, o)
+    torch.cuda.synchronize()
+    d = ulp16_diff(np_of(o), np_of(o_ref))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
+
+
+@pytest.mark.parametrize("bits,B,ctx", [(4, 64, 1024), (8, 128, 1024), (4, 5, 2500)])
+def test_live_decode_attention_full_size(dev, bits, B, ctx):
+    """Config 2 (KV4, B=64, ctx=1024, 32 q heads / 8 kv heads) and config 4 (KV8, B=128): every one of the B x 32 heads is
+    compared with the reference kernel's output on identical pages, and the appended K/V slots byte for byte.
+    Bar: |ours - ref| <= 1e-2 * max(1, |ref|) (fp16 logits / fp16 probabilities make the reference itself order dependent,
+    SURVEY.md 8c); additionally our error against float64 attention over the same cache must not exceed the reference's by
+    more than 1e-3 (we accumulate in fp32 where the reference rounds p to fp16)."""
+    ref, qb = _ref("fused_attention"), _qb()
+    from qserve_b200.decode import DecodeRunner
+
+    run = DecodeRunner("llama-3-8b", "w4a8kv4" if bits == 4 else "w8a8kv8", batch=B, ctx=ctx, device=dev, layers=1, fused=False)
+    g = torch.Generator(device=dev).manual_seed(5)
+    run.qkv_buf.copy_(torch.randn(run.qkv_buf.shape, device=dev, generator=g).half())
+    # ragged lengths: every residue of the page / slice structure occurs
+    lens = torch.randint(ctx // 2, ctx + 2, (B,), device=dev, generator=g, dtype=torch.int32)
+    lens[0], lens[-1] = ctx + 1, ctx // 2
+    D = 128
+    q, k, v = run.qkv_buf.split([run.q_size, run.kv_size, run.kv_size], dim=-1)
+    q, k, v = q.reshape(B, run.Hq, D), k.reshape(B, run.Hkv, D), v.reshape(B, run.Hkv, D)
+    snap_k, snap_v = run.kpools[0].clone(), run.vpools[0].clone()
+    args = (q, k, v, run.block_tables[0], lens, None, 8192, 64, run.size_per_token, int(lens.max()), D, run.cfg.rope_theta, True, bits == 4, True)
+    o_ref = ref.single_query_attention(*args).clone()
+    torch.cuda.synchronize()
+    k_ref, v_ref = run.kpools[0].clone(), run.vpools[0].clone()
+    run.kpools[0].copy_(snap_k); run.vpools[0].copy_(snap_v)
+    o = qb.fused_attention.single_query_attention(*args)
+    torch.cuda.synchronize()
+    of, rf = o.float(), o_ref.float()
+    assert torch.isfinite(rf).all() and torch.isfinite(of).all()
+    err = float((of - rf).abs().max())
+    assert err <= 1e-2 * max(1.0, float(rf.abs().max())), err
+    assert float((run.vpools[0] != v_ref).float().mean()) < 1e-6
+    assert float((run.kpools[0] != k_ref).float().mean()) < 1e-4  # fast-math RoPE in the reference moves a few K codes by one
+    print(f"[live attention kv{bits} B={B} ctx={ctx}] max |ours - ref| = {err:.3e}")
+
+
+def test_live_norm_quant_silu_at_model_width(dev):
+    fk, ln, act, qb = _ref("fused_kernels"), _ref("layernorm_ops"), _ref("activation_ops"), _qb()
+    g = torch.Generator(device=dev).manual_seed(9)
+    M, H, I = 64, 4096, 14336
+    x = (torch.randn((M, H), device=dev, generator=g) * 1.3 + 0.1).half()
+    gamma = (1 + 0.1 * torch.randn(H, device=dev, generator=g)).half()
+    mk = lambda w: (torch.empty((M, w), dtype=torch.int8, device=dev), torch.empty(M, dtype=torch.half, device=dev), torch.empty(M, dtype=torch.half, device=dev))
+    (q0, s0, m0), (q1, s1, m1) = mk(H), mk(H)
+    ln.rms_norm_general_fuse_sum(q0, x, gamma, m0, s0, 1e-5, True)
+    qb.layernorm_ops.rms_norm_general_fuse_sum(q1, x, gamma, m1, s1, 1e-5, True)
+    dq = (q0.int() - q1.int()).abs()
+    assert int(dq.max()) <= 1 and float((dq > 0).float().mean()) < 2e-3
+    assert ulp16_diff(np_of(s1), np_of(s0)).max() <= 1 and ulp16_diff(np_of(m1), np_of(m0)).max() <= 2
+    fk.invoke_quant_fuse_sum(q0, x, m0, s0)
+    qb.fused_kernels.invoke_quant_fuse_sum(q1, x, m1, s1)
+    dq = (q0.int() - q1.int()).abs()
+    assert int(dq.max()) <= 1 and float((dq > 0).float().mean()) < 5e-4
+    assert torch.equal(s0, s1) and ulp16_diff(np_of(m1), np_of(m0)).max() <= 1
+    gu = torch.randn((M, 2 * I), device=dev, generator=g).half()
+    a0, a1 = torch.empty((M, I), dtype=torch.half, device=dev), torch.empty((M, I), dtype=torch.half, device=dev)
+    act.silu_and_mul(a0, gu)
+    qb.activation_ops.silu_and_mul(a1, gu)
+    d = ulp16_diff(np_of(a1), np_of(a0))
+    assert d.max() <= 2 and (d > 0).mean() < 2e-3
+    o0, o1 = torch.empty_like(x), torch.empty_like(x)
+    ln.rms_norm(o0, x, gamma, 1e-5, False)
+    qb.layernorm_ops.rms_norm(o1, x, gamma, 1e-5, False)
+    assert ulp16_diff(np_of(o1), np_of(o0)).max() <= 1
+
+
+def test_lengths_none_matches_reference_semantics(dev):
+    """with length_per_sample = None the reference uses tlength = timestep (Template.hpp:901), i.e. the cache holds
+    `timestep` tokens and the new token lands in slot `timestep`.  Must equal the call with lengths = timestep + 1."""
+    qb = _qb()
+    from qserve_b200.decode import DecodeRunner
+
+    B, T = 3, 100
+    run = DecodeRunner("tiny", "w4a8kv4", batch=B, ctx=191, device=dev, layers=1, fused=False, seed=4)
+    g = torch.Generator(device=dev).manual_seed(1)
+    run.qkv_buf.copy_(torch.randn(run.qkv_buf.shape, device=dev, generator=g).half())
+    D = 128
+    q, k, v = run.qkv_buf.split([run.q_size, run.kv_size, run.kv_size], dim=-1)
+    q, k, v = q.reshape(B, run.Hq, D), k.reshape(B, run.Hkv, D), v.reshape(B, run.Hkv, D)
+    snap_k, snap_v = run.kpools[0].clone(), run.vpools[0].clone()
+    lens = torch.full((B,), T + 1, dtype=torch.int32, device=dev)
+    o1 = qb.fused_attention.single_query_attention(q, k, v, run.block_tables[0], lens, None, 8192, 64, run.size_per_token, T + 1, D, 10000.0, True, True, True)
+    k1, v1 = run.kpools[0].clone(), run.vpools[0].clone()
+    run.kpools[0].copy_(snap_k); run.vpools[0].copy_(snap_v)
+    o2 = qb.fused_attention.single_query_attention(q, k, v, run.block_tables[0], None, None, 8192, 64, run.size_per_token, T, D, 10000.0, True, True, True)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2) and torch.equal(k1, run.kpools[0]) and torch.equal(v1, run.vpools[0])
+    assert not torch.equal(k1, snap_k)  # the append really happened (slot T)
+    ref = None
+    try:
+        from tests import refmods
+        ref = refmods.load("fused_attention")
+    except Exception:  # noqa: BLE001
+        pass
+    if ref is not None:  # and the live reference agrees on where the token goes
+        run.kpools[0].copy_(snap_k); run.vpools[0].copy_(snap_v)
+        o3 = ref.single_query_attention(q, k, v, run.block_tables[0], None, None, 8192, 64, run.size_per_token, T, D, 10000.0, True, True, True)
+        torch.cuda.synchronize()
+        assert float((o3.float() - o2.float()).abs().max()) <= 1e-2 * max(1.0, float(o3.float().abs().max()))
+        assert float((run.vpools[0] != v1).float().mean()) < 1e-6
