@@ -103,6 +103,11 @@ QS_API size_t qs_attention_workspace_bytes(int batch, int num_heads, int head_di
 /* qserve_backend.fused_attention.apply_bias_rope_update_kv_cache    kernels/csrc/fused_attention/update_kv_cache.cu:20-108
  *   qkv fp16 [T,(Hq+2Hkv)*D]: q and k are rotated IN PLACE (NeoX), K/V quantised per (token, kv head) into the pages.
  *   kv_pointers may be NULL (rotate only).                                                                          */
+/* Extension: one-shot request consumed by the NEXT qs_single_query_attention[_quant] launch of this process: while the attention kernel
+ * streams the KV pages (its loop is ALU-bound at ~45 % of the HBM bandwidth) it also pre-stages up to two STATIC byte ranges -- the packed
+ * weights of the GEMMs that follow -- into L2 with cp.async.bulk.prefetch.L2, paced by its own main loop.  Pure performance hint: results
+ * are unaffected.  Pointers must be 16-byte aligned device addresses that stay valid until the launch completes; bytes = 0 disables a range. */
+QS_API int qs_attention_prefetch_next(const void* ptr0, size_t bytes0, const void* ptr1, size_t bytes1);
 QS_API int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens, const int32_t* padding_offset, const int64_t* kv_pointers,
                                        int batch, int num_tokens, int max_blocks_per_seq, int head_num, int kv_head_num, int head_dim,
                                        int seq_len, int tokens_per_block, int size_per_token, int rotary_embedding_dim,

@@ -25,6 +25,58 @@ def _unpack_dequant(qweight: np.ndarray, s1: np.ndarray, s1z: np.ndarray) -> tor
     return q.to(torch.float32) * torch.from_numpy(s1.astype(np.float32))[:, None] - torch.from_numpy(s1z.astype(np.float32))[:, None]
 
 
+class LayerSample:
+    """Inputs of one decoder layer's sample, generated ONCE (outside every timed region); `run()` does the timed CPU work.
+    Used by `bench.py --impl reference`, whose steps are bounded samples of the workload (one layer each)."""
+
+    def __init__(self, hidden: int, intermediate: int, heads: int, kv_heads: int, batch: int, ctx: int, threads: int, seed: int = 0):
+        torch.set_num_threads(threads)
+        rng = np.random.default_rng(seed)
+        D = 128
+        self.batch, self.ctx, self.heads, self.kv_heads, self.D = batch, ctx, heads, kv_heads, D
+        self.gemms = []
+        for K, N in [(hidden, (heads + 2 * kv_heads) * D), (heads * D, hidden), (hidden, 2 * intermediate), (intermediate, hidden)]:
+            qw = rng.integers(-128, 128, size=(N, K // 2), dtype=np.int8)
+            s1 = rng.uniform(0.005, 0.02, size=N).astype(np.float16)
+            s1z = (s1.astype(np.float32) * 8).astype(np.float16)
+            aq = torch.from_numpy(rng.integers(-127, 128, size=(batch, K), dtype=np.int8))
+            sa = torch.from_numpy(rng.uniform(0.01, 0.05, size=batch).astype(np.float32))
+            self.gemms.append((qw, s1, s1z, aq, sa))
+        self.codes_k = torch.from_numpy(rng.integers(0, 256, size=(batch, kv_heads, ctx, D // 2), dtype=np.uint8))
+        self.codes_v = torch.from_numpy(rng.integers(0, 256, size=(batch, kv_heads, ctx, D // 2), dtype=np.uint8))
+        self.sk = torch.from_numpy(rng.uniform(0.01, 0.1, size=(batch, kv_heads, ctx, 1)).astype(np.float32))
+        self.zk = torch.from_numpy(rng.uniform(0, 15, size=(batch, kv_heads, ctx, 1)).astype(np.float32))
+        self.q = torch.from_numpy(rng.standard_normal((batch, heads, 1, D)).astype(np.float32))
+
+    def run(self):
+        t_deq = t_mm = 0.0
+        for qw, s1, s1z, aq, sa in self.gemms:
+            t0 = time.perf_counter()
+            w = _unpack_dequant(qw, s1, s1z)
+            x = aq.to(torch.float32) * sa[:, None]
+            t1 = time.perf_counter()
+            y = (x @ w.T).to(torch.float16)
+            t2 = time.perf_counter()
+            t_deq += t1 - t0
+            t_mm += t2 - t1
+            del w, y
+        batch, kv_heads, ctx, D = self.batch, self.kv_heads, self.ctx, self.D
+        t0 = time.perf_counter()
+
+        def deq(c):
+            lo = (c & 0xF).to(torch.float32)
+            hi = (c >> 4).to(torch.float32)
+            u = torch.stack([lo, hi], dim=-1).reshape(batch, kv_heads, ctx, D)
+            return (u - self.zk) * self.sk
+
+        kf, vf = deq(self.codes_k), deq(self.codes_v)
+        g = self.heads // kv_heads
+        o = torch.nn.functional.scaled_dot_product_attention(self.q, kf.repeat_interleave(g, dim=1), vf.repeat_interleave(g, dim=1))
+        t_attn = time.perf_counter() - t0
+        del o, kf, vf
+        return {"dequant_s": t_deq, "matmul_s": t_mm, "attention_s": t_attn, "layer_s": t_deq + t_mm + t_attn}
+
+
 def layer_sample(hidden: int, intermediate: int, heads: int, kv_heads: int, batch: int, ctx: int, threads: int, seed: int = 0):
     """Time one decoder layer's worth of the hot path on the CPU.  Returns dict of seconds."""
     torch.set_num_threads(threads)

@@ -438,6 +438,14 @@ def invoke_quant_given_amax(out, input, amax: torch.Tensor, input_sum: Optional[
           scale.data_ptr(), tokens, hidden)
 
 
+def attention_prefetch_next(t0: Optional[torch.Tensor], t1: Optional[torch.Tensor] = None) -> None:
+    """One-shot hint for the next single_query_attention[_quant] call: pre-stage the (static, contiguous) tensors t0 / t1 -- the weights of
+    the GEMMs that follow -- into L2 while the attention kernel streams the KV pages.  Results are unaffected."""
+    p = lambda t: (t.data_ptr(), t.numel() * t.element_size()) if t is not None else (None, 0)
+    (a, na), (b, nb) = p(t0), p(t1)
+    check(lib.qs_attention_prefetch_next(a, na, b, nb))
+
+
 def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """torch.argmax(logits, dim=-1) for fp16 logits [rows, vocab] in one launch (greedy sampling of the decode runner)."""
     _cuda(logits, "logits")

@@ -13,6 +13,12 @@ static int g_pdl = 1;
 static int g_force_split = 0;
 static int g_force_nt = 0;
 static void* g_gemm_prof = nullptr;
+// one-shot L2 prefetch request consumed by the next decode-attention launch (qs_attention_prefetch_next)
+static const void* g_pf_ptr[2] = {nullptr, nullptr};
+static unsigned long long g_pf_bytes[2] = {0, 0};
+static void take_prefetch(DecodeAttnArgs& a) {
+  for (int r = 0; r < 2; ++r) { a.pf_ptr[r] = g_pf_ptr[r]; a.pf_bytes[r] = g_pf_bytes[r]; g_pf_ptr[r] = nullptr; g_pf_bytes[r] = 0; }
+}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -133,6 +139,7 @@ int qs_single_query_attention(const void* q, const void* k, const void* v, int64
   a.tokens_per_block = tokens_per_block; a.size_per_token = size_per_token; a.timestep = timestep; a.memory_max_len = memory_max_seqlen;
   a.rotary_dim = rotary_embedding_dim; a.rotary_base = rotary_base; a.int4_kv = int4_kv_cache; a.kv_zeros = kv_cache_with_zeros;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.prof = g_gemm_prof; a.stream = stream;
+  take_prefetch(a);
   return decode_attention(a);
 }
 
@@ -150,7 +157,14 @@ int qs_single_query_attention_quant(const void* q, const void* k, const void* v,
   a.tokens_per_block = tokens_per_block; a.size_per_token = size_per_token; a.timestep = timestep; a.memory_max_len = memory_max_seqlen;
   a.rotary_dim = rotary_embedding_dim; a.rotary_base = rotary_base; a.int4_kv = int4_kv_cache; a.kv_zeros = kv_cache_with_zeros;
   a.stream = stream;
+  take_prefetch(a);
   return decode_attention(a);
+}
+
+int qs_attention_prefetch_next(const void* ptr0, size_t bytes0, const void* ptr1, size_t bytes1) {
+  g_pf_ptr[0] = ptr0; g_pf_bytes[0] = bytes0;
+  g_pf_ptr[1] = ptr1; g_pf_bytes[1] = bytes1;
+  return 0;
 }
 
 int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens, const int32_t* padding_offset, const int64_t* kv_pointers, int batch,

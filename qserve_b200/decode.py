@@ -51,30 +51,7 @@ class OpSet:
 DEFAULT_OPS = OpSet()
 
 
-@dataclass(frozen=True)
-class ModelConfig:
-    name: str
-    hidden: int
-    intermediate: int
-    heads: int
-    kv_heads: int
-    layers: int
-    vocab: int
-    rope_theta: float
-    eps: float = 1e-5
-    head_dim: int = 128
-    max_pos: int = 8192
-
-
-MODELS = {
-    "llama-3-8b": ModelConfig("Llama-3-8B", 4096, 14336, 32, 8, 32, 128256, 500000.0),
-    "mistral-7b": ModelConfig("Mistral-7B", 4096, 14336, 32, 8, 32, 32000, 10000.0, max_pos=32768),
-    "llama-2-7b": ModelConfig("Llama-2-7B", 4096, 11008, 32, 32, 32, 32000, 10000.0, max_pos=4096),
-    "qwen1.5-72b": ModelConfig("Qwen1.5-72B", 8192, 24576, 64, 64, 80, 152064, 1000000.0, eps=1e-6, max_pos=32768),
-    "tiny": ModelConfig("tiny-test", 512, 1024, 4, 2, 2, 1024, 10000.0),
-}
-
-PRECISIONS = ("w4a8kv4", "w4a8kv4-g128", "w8a8kv8", "w4a8kv8", "w8a8kv4")
+from qserve_b200.modelcfg import MODELS, PRECISIONS, ModelConfig  # noqa: E402,F401  (pure-Python table; re-exported)
 
 
 class _Linear:
@@ -117,10 +94,11 @@ class _Linear:
 class DecodeRunner:
     def __init__(self, model: str = "llama-3-8b", precision: str = "w4a8kv4", batch: int = 64, ctx: int = 1024,
                  device: Optional[torch.device] = None, tp_rank: int = 0, tp_size: int = 1, seed: int = 0, layers: Optional[int] = None,
-                 process_group=None, fused: bool = True, ops: Optional[OpSet] = None, tp_exact: bool = False):
+                 process_group=None, fused: bool = True, ops: Optional[OpSet] = None, tp_exact: bool = False, l2_prefetch: bool = False):
         assert precision in PRECISIONS, precision
         self.ops = ops = ops or DEFAULT_OPS
         self.tp_exact = tp_exact
+        self.l2_prefetch = l2_prefetch  # the attention kernel pre-stages the following GEMMs' weights into L2 (fused path only)
         assert ops is DEFAULT_OPS or not fused, "the fused extensions exist only in this repo's library"
         self.cfg = cfg = MODELS[model]
         self.precision, self.batch, self.ctx = precision, batch, ctx
@@ -288,6 +266,8 @@ class DecodeRunner:
         for li, ly in enumerate(self.layers):
             exact = self.tp_size > 1 and self.tp_exact
             ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
+            if self.l2_prefetch and self.wmode != "w8":
+                _ext.attention_prefetch_next(ly["o"].qweight, ly["gate_up"].qweight)
             if exact:
                 self._quant(self.q_attn, self._attention(li))
             else:
