@@ -47,11 +47,11 @@ def parse():
     ap.add_argument("--no-tp", action="store_true", help="skip the Qwen1.5-72B tensor-parallel record")
     ap.add_argument("--tp-model", default="qwen1.5-72b")
     ap.add_argument("--tp-layers", type=int, default=None, help="debug only")
+    ap.add_argument("--tp-allreduce", default="peer", choices=["peer", "nccl"], help="TP record: all-reduce fused into add+norm+quant over peer memory, or NCCL")
     ap.add_argument("--tp-exact", action="store_true", help="TP record with the bit-exact parity rule (global per-token amax) instead of the throughput mode")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-fused", action="store_true", help="use exactly the reference op sequence (no fused add+norm / silu+quant extensions)")
-    ap.add_argument("--l2-prefetch", action="store_true", help="attention pre-stages the following GEMMs' weights into L2 (experiment)")
     ap.add_argument("--kernel-reps", type=int, default=5)
     return ap.parse_args()
 
@@ -208,23 +208,47 @@ def reference_arm(args, rank: int):
 # ------------------------------------------------------------------------------------------------------------
 # per-kernel timing (ours and the reference kernels go through the SAME function: only the OpSet differs)
 # ------------------------------------------------------------------------------------------------------------
-def time_kernel(fn, reps: int, stream):
+def time_kernel(fn, reps: int, stream, graph: bool = True):
+    """Seconds per launch of the launches `fn()` issues (it returns their number).  graph=True: the launches are captured ONCE into a
+    CUDA graph and the graph is replayed -- the host (ctypes marshalling, ~5-8 us per call, more than the short kernels themselves) is out of
+    the timed region and the number is the device-side cost of a launch in a dependent chain, as in the captured decode step.
+    graph=False (the reference extensions: their GEMMs launch on the legacy default stream and cannot be captured): eager back-to-back."""
     import torch
 
-    fn()  # warm
+    fn()  # warm (attributes, workspaces)
+    torch.cuda.synchronize()
+    g = None
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            n_per = fn()
+        run = g.replay
+        run()
+    else:
+        n_per = None
+        run = fn
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     n = 0
     for _ in range(reps):
-        n += fn()
+        r = run()
+        n += n_per if graph else r
     e1.record(stream)
     torch.cuda.synchronize()
+    del g
     return e0.elapsed_time(e1) * 1e-3 / n  # seconds per launch
 
 
-def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = True):
-    """Per-kernel launch duration and achieved HBM bandwidth, timed live with CUDA events on the launching stream.  Each timed
+def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = True, graph: bool = True):
+    """Per-kernel launch duration and achieved HBM bandwidth, timed live with CUDA events on the launching stream (graph replay of the
+    launch loop: see time_kernel).  Each timed
     loop walks the weights / KV pages of ALL layers (3.5 GB / 2.4 GB >> 126 MB L2), so every launch streams from HBM.
     `run.ops` decides whose kernels run (this library or the reference's)."""
     import torch
@@ -243,7 +267,7 @@ def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = Tru
             for ly in run.layers:
                 ly[name](xq, run.q_scale, run.q_sum, buf)
             return len(run.layers)
-        t = time_kernel(fn, reps, stream)
+        t = time_kernel(fn, reps, stream, graph)
         lin = run.layers[0][name]
         b = gemm_bytes(lin)
         out[f"gemm_{name}"] = {"M": M, "N": lin.N, "K": lin.K, "us": t * 1e6, "bytes": b, "GBps": b / t / 1e9, "frac": b / t / 1e9 / hbm_gbs,
@@ -257,7 +281,7 @@ def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = Tru
             ops.fused_attention.single_query_attention(q, k, v, run.block_tables[li], run.context_lens, None, min(8192, cfg.max_pos), 64, run.size_per_token,
                                                        run.max_seq_len, D, cfg.rope_theta, True, run.kv_bits == 4, True)
         return L
-    t = time_kernel(attn, reps, stream)
+    t = time_kernel(attn, reps, stream, graph)
     b = run.kv_bytes_per_step() // L
     out["attention"] = {"B": M, "Hq": run.Hq, "Hkv": run.Hkv, "ctx": run.ctx, "us": t * 1e6, "bytes": b, "GBps": b / t / 1e9, "frac": b / t / 1e9 / hbm_gbs,
                         "launches_per_step": L}
@@ -273,7 +297,7 @@ def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = Tru
             for _ in range(nrep):
                 fn()
             return nrep
-        t = time_kernel(loop, max(1, reps // 2), stream)
+        t = time_kernel(loop, max(1, reps // 2), stream, graph)
         out[name] = {"us": t * 1e6, "bytes": nbytes, "GBps": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / hbm_gbs, "launches_per_step": per_step}
 
     gam = run.layers[0]["ln1"]
@@ -298,7 +322,7 @@ def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = Tru
                 ext.single_query_attention_quant(q, k, v, run.block_tables[li], run.context_lens, min(8192, cfg.max_pos), 64, run.size_per_token, run.max_seq_len,
                                                  D, cfg.rope_theta, run.kv_bits == 4, True, run.q_attn, run.q_scale, qsum)
             return L
-        t = time_kernel(attn_q, reps, stream)
+        t = time_kernel(attn_q, reps, stream, graph)
         out["attention_quant(fused)"] = {"us": t * 1e6, "bytes": b, "GBps": b / t / 1e9, "frac": b / t / 1e9 / hbm_gbs, "launches_per_step": L}
 
     if prefill:
@@ -314,7 +338,7 @@ def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = Tru
             for ly in run.layers[:4]:
                 ly["gate_up"](xq, sc, sm, big)
             return min(4, len(run.layers))
-        t = time_kernel(pf, max(2, reps // 2), stream)
+        t = time_kernel(pf, max(2, reps // 2), stream, graph)
         opsn = 2.0 * Mp * lin.N * lin.K
         out["gemm_prefill_gate_up"] = {"M": Mp, "N": lin.N, "K": lin.K, "us": t * 1e6, "int8_TOPS": opsn / t / 1e12,
                                        "frac_of_nominal_int8_dense": opsn / t / 1e12 / 4500.0, "frac_of_measured_umma_i8_peak": opsn / t / 1e12 / 4760.0,
@@ -391,7 +415,7 @@ def reference_gpu_arm(args):
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1) / args.steps
-        kern = kernel_table(run, args.kernel_reps, hbm_gbs, prefill=True, fused_ops=False)
+        kern = kernel_table(run, args.kernel_reps, hbm_gbs, prefill=True, fused_ops=False, graph=False)
     seq = ("gemm_qkv", "gemm_o", "gemm_gate_up", "gemm_down", "attention", "norm_quant", "quant_attn_out", "quant_mlp", "silu_and_mul")
     kern_ms = sum(kern[k]["us"] * kern[k]["launches_per_step"] for k in seq) * 1e-3
     line = {"impl": "reference-gpu", "metric": metric_name(args), "value": args.batch / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1, "steps": args.steps,
@@ -494,8 +518,22 @@ def tp_block(args, rank, world, dev, hbm_gbs):
     from qserve_b200.decode import DecodeRunner
 
     cfg = model_cfg(args.tp_model)
+    want_peer = args.tp_allreduce == "peer" and world > 1 and not args.tp_exact
+    peer_err = None
+    if want_peer:
+        # symmetric memory needs CUDA VMM handle exchange between the ranks: agree on success before building the model on it
+        ok = torch.ones(1, device=dev)
+        try:
+            from qserve_b200 import backend as _b
+            probe = _b.PeerContext(8, 128, dev, dist.group.WORLD)
+            del probe
+        except Exception as e:  # noqa: BLE001
+            ok.zero_()
+            peer_err = repr(e)[:300]
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        want_peer = bool(ok.item() > 0)
     run = DecodeRunner(args.tp_model, "w4a8kv4", args.batch, args.ctx, dev, tp_rank=rank, tp_size=world, seed=rank, layers=args.tp_layers,
-                       fused=True, tp_exact=args.tp_exact)
+                       fused=True, tp_exact=args.tp_exact, tp_peer=want_peer)
     run.capture()
     stream = torch.cuda.current_stream()
     steps = max(5, min(args.steps, 20))
@@ -539,7 +577,10 @@ def tp_block(args, rank, world, dev, hbm_gbs):
            "allreduce": None if world == 1 else {"calls_per_step": 2 * L, "message_bytes": args.batch * cfg.hidden * 2, "us_per_call_isolated": ar_us,
                                                  "ms_per_step_isolated": 2 * L * ar_us * 1e-3,
                                                  "nvlink_bytes_algorithmic_per_step": 2 * L * args.batch * cfg.hidden * 2 * 2 * (world - 1) // world,
-                                                 "backend": "NCCL all-reduce inside the captured CUDA graph"},
+                                                 "us_per_call_isolated_is": "NCCL all-reduce of the same message, back to back, for reference",
+                                                 "backend": ("fused into add+norm+quant: flag exchange + 128-bit peer loads over NVLink symmetric memory (qs_add_rms_norm_general_peer), no NCCL on the data path"
+                                                             if run.tp_peer else "NCCL all-reduce inside the captured CUDA graph")},
+           "peer_fallback_reason": peer_err,
            "note": "efficiency vs TP=1 = this tokens_per_s / (N x the tp=1 record of the --gpus 1 line); 36 GB of W4 weights fit one GPU, TP is for throughput"}
     run.graph = None
     del run
@@ -576,7 +617,7 @@ def main():
 
     backend.set_pdl(not args.no_pdl)
     cfg = model_cfg(args.model)
-    run = DecodeRunner(args.model, args.precision, args.batch, args.ctx, dev, seed=rank, layers=args.layers, fused=not args.no_fused, l2_prefetch=args.l2_prefetch)
+    run = DecodeRunner(args.model, args.precision, args.batch, args.ctx, dev, seed=rank, layers=args.layers, fused=not args.no_fused)
     hbm_gbs, peak_src = peaks()
 
     # ---- pinned host buffers for the end-to-end leg ------------------------------------------------------
@@ -705,7 +746,7 @@ def main():
         "metric": metric_name(args), "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "s8", "data": "synthetic", "config": make_config(args, world),
-        "run": {"graph": not args.no_graph, "pdl": not args.no_pdl, "fused_small_ops": fused, "l2_prefetch": args.l2_prefetch,
+        "run": {"graph": not args.no_graph, "pdl": not args.no_pdl, "fused_small_ops": fused,
                 "timing": "CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"},
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": args.batch * 8 * world, "d2h_bytes_per_step": args.batch * 8 * world,
                 "ms_per_step": ms_e2e / args.steps},

@@ -103,11 +103,6 @@ QS_API size_t qs_attention_workspace_bytes(int batch, int num_heads, int head_di
 /* qserve_backend.fused_attention.apply_bias_rope_update_kv_cache    kernels/csrc/fused_attention/update_kv_cache.cu:20-108
  *   qkv fp16 [T,(Hq+2Hkv)*D]: q and k are rotated IN PLACE (NeoX), K/V quantised per (token, kv head) into the pages.
  *   kv_pointers may be NULL (rotate only).                                                                          */
-/* Extension: one-shot request consumed by the NEXT qs_single_query_attention[_quant] launch of this process: while the attention kernel
- * streams the KV pages (its loop is ALU-bound at ~45 % of the HBM bandwidth) it also pre-stages up to two STATIC byte ranges -- the packed
- * weights of the GEMMs that follow -- into L2 with cp.async.bulk.prefetch.L2, paced by its own main loop.  Pure performance hint: results
- * are unaffected.  Pointers must be 16-byte aligned device addresses that stay valid until the launch completes; bytes = 0 disables a range. */
-QS_API int qs_attention_prefetch_next(const void* ptr0, size_t bytes0, const void* ptr1, size_t bytes1);
 QS_API int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens, const int32_t* padding_offset, const int64_t* kv_pointers,
                                        int batch, int num_tokens, int max_blocks_per_seq, int head_num, int kv_head_num, int head_dim,
                                        int seq_len, int tokens_per_block, int size_per_token, int rotary_embedding_dim,
@@ -142,6 +137,15 @@ QS_API int qs_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_
  * SURVEY.md 8e parity rule: all ranks quantise their K shard of a token with the same scale.  qs_row_absmax writes the local
  * per-token max |x| (fp32 [tokens]); the caller max-all-reduces it; qs_invoke_quant_given_amax then does the arithmetic of
  * invoke_quant[_fuse_sum] with that amax (input_sum, may be null, is the LOCAL shard's row sum). */
+/* Tensor-parallel extension: the sum-all-reduce of a row-parallel GEMM output fused into its consumer ("fused into
+ * the GEMM epilogue ... over NVLink").  delta_ptrs[r] = address, valid in THIS process, of rank r's fp16 partial [tokens, hidden] of this
+ * phase (peer-mapped symmetric memory); flag_ptrs[r] = rank r's flag pad (16 x u32, zero-initialised, peer-mapped); state = 4 x u32 of
+ * local device memory, zero-initialised, owned by the library afterwards.  phase 0 / 1 = o_proj / down_proj (two buffers: see DESIGN.md 6).
+ * Semantics: delta = fp16(sum over ranks, fp32, rank order) ; then exactly qs_add_rms_norm_general(out, hidden_out, x, delta, ...).
+ * All ranks must issue the same sequence of peer calls. */
+QS_API int qs_add_rms_norm_general_peer(int8_t* out, void* hidden_out, const void* x, const void* const* delta_ptrs, void* const* flag_ptrs, void* state,
+                                        int world, int rank, int phase, const void* gamma, void* input_sum, void* scaling, float epsilon, int tokens,
+                                        int hidden, void* stream);
 QS_API int qs_row_absmax(float* amax_out, const void* input, int tokens, int hidden, void* stream);
 QS_API int qs_invoke_quant_given_amax(int8_t* out, const void* input, const float* amax, void* input_sum, void* scale, int tokens, int hidden,
                                       void* stream);

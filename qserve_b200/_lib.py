@@ -29,7 +29,6 @@ SIGNATURES = {
     "qs_single_query_attention": (c_int, [_P, _P, _P, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P, _Z, _P]),
     "qs_attention_workspace_bytes": (c_size_t, [_I, _I, _I]),
     "qs_single_query_attention_quant": (c_int, [_P, _P, _P, _L, _L, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, c_size_t, _P]),
-    "qs_attention_prefetch_next": (c_int, [_P, _Z, _P, _Z]),
     "qs_apply_bias_rope_update_kv_cache": (c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _I, _P]),
     "qs_compute_padding_offsets": (c_int, [_P, _P, _I, _I, _P]),
     "qs_rms_norm": (c_int, [_P, _P, _P, _F, _I, _I, _I, _P]),
@@ -39,6 +38,7 @@ SIGNATURES = {
     "qs_invoke_quant": (c_int, [_P, _P, _P, _I, _I, _P]),
     "qs_invoke_quant_scalar": (c_int, [_P, _P, _F, _I, _I, _P]),
     "qs_invoke_quant_fuse_sum": (c_int, [_P, _P, _P, _P, _I, _I, _P]),
+    "qs_add_rms_norm_general_peer": (c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _I, _I, _P]),
     "qs_row_absmax": (c_int, [_P, _P, _I, _I, _P]),
     "qs_invoke_quant_given_amax": (c_int, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "qs_invoke_dequant_add_residual": (c_int, [_P, _P, _P, _P, _F, _I, _I, _P]),

@@ -417,6 +417,47 @@ def single_query_attention_quant(q, k, v, kv_pointers, length_per_sample, memory
                                               ws.data_ptr(), ws.numel())
 
 
+class PeerContext:
+    """Peer-mapped buffers of a tensor-parallel group for the fused all-reduce (qs_add_rms_norm_general_peer): built once from
+    torch.distributed._symmetric_memory (device memory + NVLink peer mappings are torch's plumbing; the kernel is ours).
+    Layout of the symmetric allocation on every rank: [2 phases][tokens, hidden] fp16 partial outputs, then a 256-byte flag pad."""
+
+    def __init__(self, tokens: int, hidden: int, device: torch.device, group):
+        import ctypes
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        _require(self.world <= 8, "PeerContext: at most 8 ranks")
+        self.tokens, self.hidden = tokens, hidden
+        phase_bytes = tokens * hidden * 2
+        with torch.cuda.device(device):
+            self.buf = symm.empty(2 * phase_bytes + 256, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+            self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's pad is zeroed before anyone signals
+        base = [int(p) for p in self.handle.buffer_ptrs]
+        self.partial = [self.buf[p * phase_bytes:(p + 1) * phase_bytes].view(torch.float16).view(tokens, hidden) for p in range(2)]  # local GEMM outputs
+        arr = ctypes.c_void_p * self.world
+        self._delta = [arr(*[b + p * phase_bytes for b in base]) for p in range(2)]
+        self._flags = arr(*[b + 2 * phase_bytes for b in base])
+
+
+def add_rms_norm_general_peer(out, hidden_out, x, ctx: "PeerContext", phase: int, weight, input_sum: Optional[torch.Tensor], scaling, epsilon: float) -> None:
+    """add_rms_norm_general with delta = the sum over the tensor-parallel ranks of ctx.partial[phase] (fused all-reduce over peer memory)."""
+    _cuda(x, "x"); _half_only(x, "add_rms_norm_general_peer")
+    if _noop(x):
+        return
+    tokens, hidden = _rows(x)
+    _require(tokens == ctx.tokens and hidden == ctx.hidden, "add_rms_norm_general_peer: shape does not match the PeerContext")
+    _call(x, lib.qs_add_rms_norm_general_peer, out.data_ptr(), hidden_out.data_ptr(), x.data_ptr(), ctx._delta[phase], ctx._flags, ctx.state.data_ptr(),
+          ctx.world, ctx.rank, int(phase), weight.data_ptr(), input_sum.data_ptr() if input_sum is not None else None, scaling.data_ptr(), float(epsilon),
+          tokens, hidden)
+
+
 def row_absmax(amax_out: torch.Tensor, input: torch.Tensor) -> None:
     """Tensor-parallel extension: amax_out[t] (fp32) = max |input[t, :]| of this rank's shard (then max-all-reduced by the caller)."""
     _cuda(input, "input"); _half_only(input, "row_absmax")
@@ -436,14 +477,6 @@ def invoke_quant_given_amax(out, input, amax: torch.Tensor, input_sum: Optional[
     tokens, hidden = _rows(input)
     _call(input, lib.qs_invoke_quant_given_amax, out.data_ptr(), input.data_ptr(), amax.data_ptr(), input_sum.data_ptr() if input_sum is not None else None,
           scale.data_ptr(), tokens, hidden)
-
-
-def attention_prefetch_next(t0: Optional[torch.Tensor], t1: Optional[torch.Tensor] = None) -> None:
-    """One-shot hint for the next single_query_attention[_quant] call: pre-stage the (static, contiguous) tensors t0 / t1 -- the weights of
-    the GEMMs that follow -- into L2 while the attention kernel streams the KV pages.  Results are unaffected."""
-    p = lambda t: (t.data_ptr(), t.numel() * t.element_size()) if t is not None else (None, 0)
-    (a, na), (b, nb) = p(t0), p(t1)
-    check(lib.qs_attention_prefetch_next(a, na, b, nb))
 
 
 def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -15,7 +15,6 @@
 // CTA.  RoPE of q/k, KV quantisation and the page append of the new token are fused in; optionally also the per-token
 // INT8 quantisation of the output row (single_query_attention_quant).
 #include <math_constants.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "launch.h"
@@ -27,11 +26,6 @@ constexpr int kD = 128;          // head dim (the reference only instantiates Dh
 constexpr int kWarps = 4;
 constexpr int kChunk = 16;       // tokens per warp iteration
 constexpr int kMaxG = 8;         // query heads per CTA (rows of the m16 tile that carry data)
-
-struct PrefetchRanges {
-  const uint8_t* p[2];
-  unsigned long long n[2];
-};
 
 struct PageGeom {
   int tokens_per_block;   // 64
@@ -136,7 +130,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
                         long long k_stride, long long v_stride, const long long* __restrict__ kv_pointers, const int* __restrict__ lengths,
                         __half* __restrict__ out, int num_heads, int num_kv_heads, int max_blocks, PageGeom pg, float rotary_base, int rotary_dim,
                         int timestep, int nsplit, float* __restrict__ ws_part, uint32_t* __restrict__ ws_cnt, uint32_t* __restrict__ tok_cnt, int8_t* __restrict__ q_out,
-                        __half* __restrict__ q_scale, __half* __restrict__ q_sum, unsigned long long* __restrict__ prof, const PrefetchRanges pf) {
+                        __half* __restrict__ q_scale, __half* __restrict__ q_sum, unsigned long long* __restrict__ prof) {
   using SL = StageLayout<BITS>;
   constexpr int R = SL::kStages;
   const int G = num_heads / num_kv_heads;
@@ -188,7 +182,6 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
   uint8_t* my_ring = s_ring + warp * SL::kWarpBytes;
   uint64_t* my_full = &s_full[warp][0];
   const int zoff = pg.num_kv_heads * pg.tokens_per_block * 2;  // bytes from a scale row to the zero row
-  const uint64_t kv_policy = policy_evict_first();
   long long kp_l = 0, vp_l = 0;  // lane l: page pointers of this warp's page (batch * 32 + l)
   auto load_ptr_batch = [&](int j0) {
     const int pidx = my_first + 2 * (j0 + lane);
@@ -203,34 +196,14 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       uint8_t* dst = my_ring + slot * SL::kBytes;
       fence_proxy_async();  // the slot was last read through the generic proxy
       mbar_expect_tx(&my_full[slot], SL::kBytes);
-      // the pages are streamed once per step: evict-first keeps them from displacing the (pre-staged) weights in L2
-      bulk_copy_g2s_hint(dst + SL::kOffK, kpage + static_cast<size_t>(hk) * SL::kCodes + hslice * SL::kSliceCodes, SL::kSliceCodes, &my_full[slot], kv_policy);
-      bulk_copy_g2s_hint(dst + SL::kOffV, vpage + static_cast<size_t>(hk) * SL::kCodes + hslice * SL::kSliceCodes, SL::kSliceCodes, &my_full[slot], kv_policy);
+      bulk_copy_g2s(dst + SL::kOffK, kpage + static_cast<size_t>(hk) * SL::kCodes + hslice * SL::kSliceCodes, SL::kSliceCodes, &my_full[slot]);
+      bulk_copy_g2s(dst + SL::kOffV, vpage + static_cast<size_t>(hk) * SL::kCodes + hslice * SL::kSliceCodes, SL::kSliceCodes, &my_full[slot]);
       const uint8_t* kmeta = kpage + pg.code_bytes + hk * 128 + hslice * 64;
       const uint8_t* vmeta = vpage + pg.code_bytes + hk * 128 + hslice * 64;
       bulk_copy_g2s(dst + SL::kOffKs, kmeta, 64, &my_full[slot]);
       bulk_copy_g2s(dst + SL::kOffKz, kmeta + zoff, 64, &my_full[slot]);
       bulk_copy_g2s(dst + SL::kOffVs, vmeta, 64, &my_full[slot]);
       bulk_copy_g2s(dst + SL::kOffVz, vmeta + zoff, 64, &my_full[slot]);
-    }
-  };
-  // L2 pre-staging of the following GEMMs' (static) weights: this CTA owns an equal slice of each range, warp w a quarter of it,
-  // issued in n_my (or 1) instalments of 16-byte multiples so that the prefetch stream is paced by the attention loop itself
-  const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z;
-  const unsigned cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  auto prefetch_instalment = [&](int j, int n_inst) {
-    if (lane != 0) return;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (pf.n[r] == 0) continue;
-      const unsigned long long per_warp = (((pf.n[r] + static_cast<unsigned long long>(n_ctas) * kWarps - 1) / (static_cast<unsigned long long>(n_ctas) * kWarps)) + 15ull) & ~15ull;
-      const unsigned long long per_inst = (((per_warp + n_inst - 1) / n_inst) + 15ull) & ~15ull;
-      unsigned long long lo = (static_cast<unsigned long long>(cta_lin) * kWarps + warp) * per_warp + static_cast<unsigned long long>(j) * per_inst;
-      unsigned long long hi = lo + per_inst;
-      const unsigned long long cap = (static_cast<unsigned long long>(cta_lin) * kWarps + warp + 1) * per_warp;
-      if (hi > cap) hi = cap;
-      if (hi > pf.n[r]) hi = pf.n[r] & ~15ull;
-      for (; lo < hi; lo += 8192ull) bulk_prefetch_l2(pf.p[r] + lo, static_cast<uint32_t>(hi - lo < 8192ull ? hi - lo : 8192ull));
     }
   };
   load_ptr_batch(0);
@@ -550,10 +523,8 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
         if (((j + R) & 31) == 0) load_ptr_batch(j + R);
         issue(j + R, s);
       }
-      prefetch_instalment(j, n_my);
       if (++s == R) { s = 0; ph ^= 1; }
     }
-    if (n_my == 0) prefetch_instalment(0, 1);
 
     if (threadIdx.x == 0) ATTN_PROF(6);
     // ---- per-warp partials -> the warp's own (drained) ring: no need to wait for the other warps ----
@@ -899,16 +870,12 @@ int decode_attention(const DecodeAttnArgs& a) {
   // context splits: enough CTAs to fill the machine (4 resident CTAs per SM), never more than one split per 256 tokens
   int nsplit = 1;
   const int ctas = gx * a.batch;
-  const int slots = 148 * 4;
+  const int slots = num_sms() * 4;
   if (2 * ctas <= slots && a.timestep > 512) {
     nsplit = (slots + ctas - 1) / ctas;
     const int cap = (a.timestep + 255) / 256;
     if (nsplit > cap) nsplit = cap;
     if (nsplit > 32) nsplit = 32;
-  }
-  {
-    static const int forced = [] { const char* e = getenv("QS_ATTN_SPLIT"); return e ? atoi(e) : 0; }();  // tuning hook
-    if (forced > 0 && a.timestep > 128 * forced) nsplit = forced > 32 ? 32 : forced;
   }
   float* part = nullptr;
   uint32_t* cnt = nullptr;
@@ -934,11 +901,6 @@ int decode_attention(const DecodeAttnArgs& a) {
     out = static_cast<uint8_t*>(a.workspace) + kAttnCounterBytes + part_bytes;
   }
   dim3 grid(gx, a.batch, nsplit);
-  PrefetchRanges pf{};
-  for (int r = 0; r < 2; ++r) {
-    pf.p[r] = static_cast<const uint8_t*>(a.pf_ptr[r]);
-    pf.n[r] = (a.pf_ptr[r] && (reinterpret_cast<uintptr_t>(a.pf_ptr[r]) & 15) == 0) ? a.pf_bytes[r] : 0ull;
-  }
   auto run = [&](auto kern, size_t smem) {
     static bool attr_done[2][kMaxDevices] = {};
     bool& done = attr_done[a.int4_kv ? 0 : 1][device_ordinal()];
@@ -964,7 +926,7 @@ int decode_attention(const DecodeAttnArgs& a) {
     return check_cuda(cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(a.q),
                       static_cast<const __half*>(a.k), static_cast<const __half*>(a.v), a.q_stride, a.k_stride, a.v_stride, a.kv_pointers, a.lengths,
                       static_cast<__half*>(out), a.num_heads, a.num_kv_heads, a.max_blocks, pg, a.rotary_base, a.rotary_dim, a.timestep, nsplit,
-                      part, cnt, tok_cnt, static_cast<int8_t*>(a.q_out), static_cast<__half*>(a.q_scale), static_cast<__half*>(a.q_sum), static_cast<unsigned long long*>(a.prof), pf), "single_query_attention");
+                      part, cnt, tok_cnt, static_cast<int8_t*>(a.q_out), static_cast<__half*>(a.q_scale), static_cast<__half*>(a.q_sum), static_cast<unsigned long long*>(a.prof)), "single_query_attention");
   };
   QS_REQUIRE(a.tokens_per_block == kPageTokens, "single_query_attention: tokens_per_block=%d, only 64 is supported (cache_engine block_size)", a.tokens_per_block);
   return a.int4_kv ? run(decode_attention_kernel<4>, static_cast<size_t>(kWarps) * StageLayout<4>::kWarpBytes)

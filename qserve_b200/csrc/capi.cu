@@ -13,12 +13,6 @@ static int g_pdl = 1;
 static int g_force_split = 0;
 static int g_force_nt = 0;
 static void* g_gemm_prof = nullptr;
-// one-shot L2 prefetch request consumed by the next decode-attention launch (qs_attention_prefetch_next)
-static const void* g_pf_ptr[2] = {nullptr, nullptr};
-static unsigned long long g_pf_bytes[2] = {0, 0};
-static void take_prefetch(DecodeAttnArgs& a) {
-  for (int r = 0; r < 2; ++r) { a.pf_ptr[r] = g_pf_ptr[r]; a.pf_bytes[r] = g_pf_bytes[r]; g_pf_ptr[r] = nullptr; g_pf_bytes[r] = 0; }
-}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -139,7 +133,6 @@ int qs_single_query_attention(const void* q, const void* k, const void* v, int64
   a.tokens_per_block = tokens_per_block; a.size_per_token = size_per_token; a.timestep = timestep; a.memory_max_len = memory_max_seqlen;
   a.rotary_dim = rotary_embedding_dim; a.rotary_base = rotary_base; a.int4_kv = int4_kv_cache; a.kv_zeros = kv_cache_with_zeros;
   a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.prof = g_gemm_prof; a.stream = stream;
-  take_prefetch(a);
   return decode_attention(a);
 }
 
@@ -157,14 +150,7 @@ int qs_single_query_attention_quant(const void* q, const void* k, const void* v,
   a.tokens_per_block = tokens_per_block; a.size_per_token = size_per_token; a.timestep = timestep; a.memory_max_len = memory_max_seqlen;
   a.rotary_dim = rotary_embedding_dim; a.rotary_base = rotary_base; a.int4_kv = int4_kv_cache; a.kv_zeros = kv_cache_with_zeros;
   a.stream = stream;
-  take_prefetch(a);
   return decode_attention(a);
-}
-
-int qs_attention_prefetch_next(const void* ptr0, size_t bytes0, const void* ptr1, size_t bytes1) {
-  g_pf_ptr[0] = ptr0; g_pf_bytes[0] = bytes0;
-  g_pf_ptr[1] = ptr1; g_pf_bytes[1] = bytes1;
-  return 0;
 }
 
 int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens, const int32_t* padding_offset, const int64_t* kv_pointers, int batch,
@@ -227,6 +213,12 @@ int qs_invoke_quant_fuse_sum(int8_t* out, const void* input, void* input_sum, vo
   QS_REQUIRE(out && input && scale && input_sum, "invoke_quant_fuse_sum: null tensor");
   QS_REQUIRE(aligned16(out) && aligned16(input), "invoke_quant_fuse_sum: tensors must be 16-byte aligned");
   return quant_per_token(out, input, input_sum, scale, tokens, hidden, stream);
+}
+int qs_add_rms_norm_general_peer(int8_t* out, void* hidden_out, const void* x, const void* const* delta_ptrs, void* const* flag_ptrs, void* state, int world,
+                                 int rank, int phase, const void* gamma, void* input_sum, void* scaling, float epsilon, int tokens, int hidden, void* stream) {
+  QS_REQUIRE(out && hidden_out && x && delta_ptrs && flag_ptrs && state && gamma && scaling, "add_rms_norm_general_peer: null tensor");
+  QS_REQUIRE(aligned16(out) && aligned16(hidden_out) && aligned16(x) && aligned16(gamma), "add_rms_norm_general_peer: tensors must be 16-byte aligned");
+  return add_layernorm_quant_peer(out, hidden_out, x, delta_ptrs, flag_ptrs, state, world, rank, phase, gamma, input_sum, scaling, epsilon, tokens, hidden, stream);
 }
 int qs_row_absmax(float* amax_out, const void* input, int tokens, int hidden, void* stream) {
   QS_REQUIRE(amax_out && input, "row_absmax: null tensor");

@@ -156,10 +156,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tmap, int32_t x, int32_t y) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y) : "memory");
 }
-// fire-and-forget HBM -> L2 prefetch of a linear range (bytes: multiple of 16); no shared-memory destination, no barrier
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

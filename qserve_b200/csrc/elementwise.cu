@@ -183,10 +183,39 @@ __global__ void __launch_bounds__(kThreads) layernorm_quant_kernel(int8_t* __res
 constexpr int kFusedThreads = kThreads;  // same thread count and loop order as the unfused kernels -> bit-identical sums
 
 constexpr int kGammaPre = 4;  // gamma chunks (8 halves each) a thread keeps in registers: covers H <= 8192 at 256 threads
+
+// Tensor parallelism: the sum-all-reduce of the row-parallel GEMM output FUSED into the consumer (residual add + norm + quant).
+// Every rank's GEMM writes its fp16 partial [M, H] into a peer-mapped (NVLink / NVSwitch symmetric-memory) buffer; this kernel
+//   1. (after its own GEMM is complete: griddepcontrol.wait) raises a flag in every peer's flag pad:  flags[r][phase * 8 + me] = epoch,
+//   2. waits until all peers' flags have reached the epoch in ITS pad (their partials are complete),
+//   3. pulls the token row of all ranks with 128-bit peer loads, sums them in fp32 IN RANK ORDER (every rank computes the same bits),
+//      rounds once to fp16 -- the value an fp16 all-reduce would have delivered, without its per-hop roundings -- and continues as
+//      add_rms_norm_general.  No NCCL call, no extra kernel boundary, the NVLink transfer overlaps the other rows' norm arithmetic.
+// Two phases (o_proj / down_proj) use two buffers, so a rank that runs ahead can never overwrite a partial a slower peer still reads:
+// buffer p is rewritten only after a kernel that waited for the peers' NEXT-phase flags.
+struct PeerArgs {
+  const __half* delta[8];   // partial-output buffer of this phase on every rank (peer-mapped addresses), indexed by rank
+  uint32_t* flags[8];       // flag pad of every rank (peer-mapped): 16 x u32, [phase * 8 + source rank]
+  uint32_t* state;          // local: [phase] = epoch of the last completed launch, [2 + phase] = finished-CTA counter
+  int world, rank, phase;
+};
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {  // peer memory: bypass the (incoherent) L1
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool PEER>
 __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8_t* __restrict__ out, __half* __restrict__ hidden_out,
                                                                            const __half* __restrict__ x, const __half* __restrict__ delta,
                                                                            const __half* __restrict__ gamma, __half* __restrict__ input_sum,
-                                                                           __half* __restrict__ scaling, float eps, int H, int ref_block) {
+                                                                           __half* __restrict__ scaling, float eps, int H, int ref_block, const PeerArgs peer) {
   extern __shared__ __align__(16) uint8_t sm[];
   __half* sx = reinterpret_cast<__half*>(sm);
   __half* sy = sx + H;
@@ -204,12 +233,55 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
   }
   pdl_wait();
   qs_trace(QS_K_ADDNORM, 1);
+  uint32_t epoch = 0;
+  if constexpr (PEER) {
+    epoch = *reinterpret_cast<volatile uint32_t*>(peer.state + peer.phase) + 1u;
+    if (blockIdx.x == 0 && threadIdx.x < peer.world) st_release_sys(peer.flags[threadIdx.x] + peer.phase * 8 + peer.rank, epoch);
+    if (threadIdx.x < peer.world) {
+      const uint32_t* mine = peer.flags[peer.rank] + peer.phase * 8 + threadIdx.x;
+      unsigned spins = 0;
+      while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
+        __nanosleep(40);
+        if (++spins > (1u << 27)) {  // several seconds: a peer died or the ranks disagree on the launch sequence
+          printf("qserve_b200: peer all-reduce timed out (rank %d waits for rank %d, phase %d, epoch %u)\n", peer.rank, threadIdx.x, peer.phase, epoch);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+  }
   {
     const uint4* a = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H);
     const uint4* b = reinterpret_cast<const uint4*>(delta + static_cast<size_t>(row) * H);
     uint4* ho = reinterpret_cast<uint4*>(hidden_out + static_cast<size_t>(row) * H);
     for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
-      const uint4 va = __ldg(a + i), vb = __ldg(b + i);
+      const uint4 va = __ldg(a + i);
+      uint4 vb;
+      if constexpr (PEER) {
+        // all ranks' partials of this 16-byte column chunk: issue every peer load first, then sum in rank order (fp32), round once
+        uint4 pv[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < peer.world) pv[r] = ld_peer_v4(reinterpret_cast<const uint4*>(peer.delta[r] + static_cast<size_t>(row) * H) + i);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r < peer.world) {
+            const __half2* hp = reinterpret_cast<const __half2*>(&pv[r]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(hp[j]);
+              acc[2 * j] = __fadd_rn(acc[2 * j], f.x);
+              acc[2 * j + 1] = __fadd_rn(acc[2 * j + 1], f.y);
+            }
+          }
+        }
+        __half2* hb2 = reinterpret_cast<__half2*>(&vb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hb2[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+      } else {
+        vb = __ldg(b + i);
+      }
       uint4 vo;
       const __half2* ha = reinterpret_cast<const __half2*>(&va);
       const __half2* hb = reinterpret_cast<const __half2*>(&vb);
@@ -297,6 +369,16 @@ __global__ void __launch_bounds__(kFusedThreads) add_layernorm_quant_kernel(int8
     if (i < H / 8) quant_chunk(i, gpre[e]);
   }
   for (int i = threadIdx.x + kGammaPre * blockDim.x; i < H / 8; i += blockDim.x) quant_chunk(i, __ldg(reinterpret_cast<const uint4*>(gamma) + i));
+  if constexpr (PEER) {
+    // the last CTA of the launch to get here publishes the epoch for the next launch of this phase (stream order separates the two)
+    if (threadIdx.x == 0) {
+      const uint32_t old = atomicAdd(peer.state + 2 + peer.phase, 1u);
+      if (old == gridDim.x - 1) {
+        peer.state[2 + peer.phase] = 0u;
+        *reinterpret_cast<volatile uint32_t*>(peer.state + peer.phase) = epoch;
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ __half silu_h_fused(__half x) {
@@ -878,13 +960,36 @@ int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void
   if (tokens == 0) return QS_OK;
   QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "add_rms_norm_general: hidden=%d must be a positive multiple of 8", hidden);
   const size_t smem = static_cast<size_t>(hidden) * 2 * (input_sum ? 2 : 1);
-  int rc = ensure_smem(add_layernorm_quant_kernel, smem, "add_rms_norm_general");
+  int rc = ensure_smem(add_layernorm_quant_kernel<false>, smem, "add_rms_norm_general");
   if (rc) return rc;
   int ref_block = hidden < 1024 ? hidden : 1024;
   ref_block = 32 * ((ref_block + 31) / 32);
-  return launch(add_layernorm_quant_kernel, dim3(tokens), dim3(kFusedThreads), smem, stream, "add_rms_norm_general", static_cast<int8_t*>(out_q),
+  return launch(add_layernorm_quant_kernel<false>, dim3(tokens), dim3(kFusedThreads), smem, stream, "add_rms_norm_general", static_cast<int8_t*>(out_q),
                 static_cast<__half*>(hidden_out), static_cast<const __half*>(x), static_cast<const __half*>(delta),
-                static_cast<const __half*>(gamma), static_cast<__half*>(input_sum), static_cast<__half*>(scaling), eps, hidden, ref_block);
+                static_cast<const __half*>(gamma), static_cast<__half*>(input_sum), static_cast<__half*>(scaling), eps, hidden, ref_block, PeerArgs{});
+}
+
+int add_layernorm_quant_peer(void* out_q, void* hidden_out, const void* x, const void* const* delta_ptrs, void* const* flag_ptrs, void* state, int world,
+                             int rank, int phase, const void* gamma, void* input_sum, void* scaling, float eps, int tokens, int hidden, void* stream) {
+  if (tokens == 0) return QS_OK;
+  QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "add_rms_norm_general_peer: hidden=%d must be a positive multiple of 8", hidden);
+  QS_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && (phase == 0 || phase == 1), "add_rms_norm_general_peer: world=%d rank=%d phase=%d", world, rank, phase);
+  PeerArgs pa{};
+  for (int r = 0; r < world; ++r) {
+    QS_REQUIRE(delta_ptrs[r] && flag_ptrs[r] && (reinterpret_cast<uintptr_t>(delta_ptrs[r]) & 15) == 0, "add_rms_norm_general_peer: bad peer pointer of rank %d", r);
+    pa.delta[r] = static_cast<const __half*>(delta_ptrs[r]);
+    pa.flags[r] = static_cast<uint32_t*>(flag_ptrs[r]);
+  }
+  pa.state = static_cast<uint32_t*>(state);
+  pa.world = world; pa.rank = rank; pa.phase = phase;
+  const size_t smem = static_cast<size_t>(hidden) * 2 * (input_sum ? 2 : 1);
+  int rc = ensure_smem(add_layernorm_quant_kernel<true>, smem, "add_rms_norm_general_peer");
+  if (rc) return rc;
+  int ref_block = hidden < 1024 ? hidden : 1024;
+  ref_block = 32 * ((ref_block + 31) / 32);
+  return launch(add_layernorm_quant_kernel<true>, dim3(tokens), dim3(kFusedThreads), smem, stream, "add_rms_norm_general_peer", static_cast<int8_t*>(out_q),
+                static_cast<__half*>(hidden_out), static_cast<const __half*>(x), static_cast<const __half*>(nullptr),
+                static_cast<const __half*>(gamma), static_cast<__half*>(input_sum), static_cast<__half*>(scaling), eps, hidden, ref_block, pa);
 }
 
 int argmax_rows(void* out, const void* logits, int rows, int vocab, void* stream) {

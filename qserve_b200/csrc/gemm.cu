@@ -27,9 +27,11 @@
 //     weight stream.
 //   * epilogue fused: acc*s1[n]*sa[m] - s1z[n]*asum[m] (per-channel) or acc*(s1[n]*sa[m]) (per-group, W8A8) -> fp16,
 //     IEEE fp32 in the reference's source order (bit-exact against the oracle).
-//   * gemm_wide_kernel (opt-in): a band-partitioned one-CTA-per-SM variant for layers with more tiles than SMs.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "launch.h"
@@ -60,7 +62,6 @@ struct GemmParams {
   int M, N, K;
   int m_tiles, kb_per_tile, split;
   unsigned long long* prof;  // optional: 16 globaltimer stamps per CTA (tools/gemm_timeline.py)
-  const uint8_t* w;          // wide kernel: packed INT4 weights (bulk copies address the bands directly)
 };
 
 // WS = depth of the WEIGHT ring in shared memory.  Weights are static, so the producer streams them before the
@@ -494,291 +495,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
-// =============================================================================================
-// Wide layers at decode size (more 128-channel tiles than SMs: gate_up_proj, 224 tiles on 148 SMs).
-//
-// One CTA per SM owns a contiguous range of 6..8 of the N/32 weight BANDS (a band = 32 channels, contiguous in K) for the
-// whole K range: every SM streams the same number of bytes (no second-wave stragglers) and reads the activations once per
-// ~200 channels instead of once per 128.  Bands 0..3 of the range accumulate in TMEM accumulator 0, bands 4..7 in
-// accumulator 1 (two M = 128 UMMAs per k-step share the activation operand); the packed weights arrive by one 4 KB
-// cp.async.bulk per band and 256-K stage (no tensor map: the checkpoint layout is contiguous per band).
-// Per-channel W4A8 only (the headline configuration); everything else uses gemm_kernel above.
-// =============================================================================================
-constexpr int kWideThreads = 384;  // W producer | MMA | 2 x 4 unpack/epilogue warps | activation producer | spare
-template <int NT, int WS, int AS>
-struct WideCfg {
-  static constexpr int kBands = 8;                       // band slots per CTA (two accumulators x four TMEM lane quadrants)
-  static constexpr int kBandStage = kSub * 2048;         // packed bytes of one band for one 256-K stage
-  static constexpr int kWStage = kBands * kBandStage;    // 32 KB
-  static constexpr int kActSub = NT * kBK;
-  static constexpr int kActBytes = kSub * kActSub;
-  static constexpr int kTA = 3;                          // unpacked-A ring in tensor memory (128 columns per stage)
-  static constexpr int kAStageCols = 2 * kSub * (kBK / 4);
-  static constexpr int kTmemNeed = 2 * NT + kTA * kAStageCols;
-  static constexpr int kTmemCols = 512;
-  static_assert(kTmemNeed <= 512, "TMEM overflow");
-  static constexpr int kOffAct = 0;
-  static constexpr int kOffW = AS * kActBytes;
-  static constexpr int kPipeBytes = kOffW + WS * kWStage;
-  static constexpr int kRedBytes = NT * 2 * kBM * 4;     // INT32 tile [NT][256]
-  static constexpr int kOffRow = (kPipeBytes > kRedBytes ? kPipeBytes : kRedBytes);
-  static constexpr int kOffBar = kOffRow + 2 * NT * 4;
-  static constexpr int kNumBars = 2 * WS + 2 * AS + 2 * kTA + 2;
-  static constexpr int kOffMisc = kOffBar + kNumBars * 8;
-  static constexpr int kSmemBytes = kOffMisc + 16;
-  static_assert(kSmemBytes <= 226 * 1024, "shared memory overflow");
-};
-
-template <int NT, int WS, int AS, bool ACC>
-__global__ void __launch_bounds__(kWideThreads, 1)
-gemm_wide_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w_lo,
-                 const __grid_constant__ CUtensorMap tmap_w_hi, const GemmParams p) {
-  using C = WideCfg<NT, WS, AS>;
-  constexpr int TA = C::kTA;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* s_act = smem + C::kOffAct;
-  uint8_t* s_w = smem + C::kOffW;
-  int32_t* s_red = reinterpret_cast<int32_t*>(smem);  // [NT][256], aliases the pipeline buffers once the mainloop has drained
-  float* s_asc = reinterpret_cast<float*>(smem + C::kOffRow);
-  float* s_asum = s_asc + NT;
-  uint64_t* bar_wfull = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
-  uint64_t* bar_wempty = bar_wfull + WS;
-  uint64_t* bar_xfull = bar_wempty + WS;
-  uint64_t* bar_xempty = bar_xfull + AS;
-  uint64_t* bar_afull = bar_xempty + AS;
-  uint64_t* bar_aempty = bar_afull + TA;
-  uint64_t* bar_dfull = bar_aempty + TA;
-  uint64_t* bar_zero = bar_dfull + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kOffMisc);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int bands_total = p.N / 32;
-  const int G = static_cast<int>(gridDim.x);
-  const int b0 = static_cast<int>((static_cast<long long>(bands_total) * blockIdx.x) / G);
-  const int b1 = static_cast<int>((static_cast<long long>(bands_total) * (blockIdx.x + 1)) / G);
-  const int nb = b1 - b0;                       // 1..8 bands
-  const int ksub_total = p.K / kBK;             // 128-K sub-blocks
-  const int n_kb = (ksub_total + kSub - 1) / kSub;
-  if (threadIdx.x == 0) QS_PROF(0);
-  qs_trace(QS_K_GEMM, 0);
-  // final-phase geometry: thread -> channel pair pr of the CTA's range (its static scales are fetched now)
-  const int pr = static_cast<int>(threadIdx.x) & 127;
-  const bool pr_ok = pr < nb * 16;
-  const int n_ch = b0 * 32 + 2 * pr;
-  __half2 ws_h2 = __half2half2(__ushort_as_half(0)), wz_h2 = ws_h2;
-  if (pr_ok) {
-    ws_h2 = __ldg(reinterpret_cast<const __half2*>(p.wscales + n_ch));
-    wz_h2 = __ldg(reinterpret_cast<const __half2*>(p.w_szs + n_ch));
-  }
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_act);
-    for (int i = 0; i < WS; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 8); }
-    for (int i = 0; i < AS; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
-    for (int i = 0; i < TA; ++i) { mbar_init(&bar_afull[i], 8); mbar_init(&bar_aempty[i], 1); }
-    mbar_init(bar_dfull, 2);  // two MMA issuers
-    mbar_init(bar_zero, 8);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<C::kTmemCols>(s_tmem);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-  if (threadIdx.x == 0) { pdl_launch_dependents(); QS_PROF(1); }
-  auto subs_of = [&](int it) { return min(kSub, ksub_total - it * kSub); };
-
-  if (warp == 0) {
-    // ===================================== weight producer: never waits for the previous kernel =====================================
-    if (lane == 0) {
-      // two tensor maps over [N/32 bands][K * 16 B] (u64 elements) whose boxes are floor / ceil (bands / CTAs) bands high:
-      // ONE tensor copy per 128-K sub-block brings all bands of this CTA (a per-band bulk copy costs ~100 ns of issue time each)
-      const int nb_lo = bands_total / G;
-      const CUtensorMap* tm = (nb == nb_lo) ? &tmap_w_lo : &tmap_w_hi;
-      tma_prefetch_desc(tm);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_kb; ++it) {
-        if (it >= WS) mbar_wait(&bar_wempty[s], ph);
-        const int subs = subs_of(it);
-        mbar_expect_tx(&bar_wfull[s], static_cast<uint32_t>(subs * nb) * 2048u);
-        for (int u = 0; u < subs; ++u) tma_load_2d(s_w + s * C::kWStage + u * (C::kBands * 2048), tm, (it * kSub + u) * 256, b0, &bar_wfull[s]);
-        if (++s == WS) { s = 0; if (it >= WS) ph ^= 1; }
-      }
-      QS_PROF(3);
-    }
-  } else if (warp == 10) {
-    // ===================================== activation producer =====================================
-    if (lane == 0) {
-      pdl_wait();
-      QS_PROF(2);
-      qs_trace(QS_K_GEMM, 1, 10 * 32);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_kb; ++it) {
-        if (it >= AS) mbar_wait(&bar_xempty[s], ph);
-        const int subs = subs_of(it);
-        mbar_expect_tx(&bar_xfull[s], static_cast<uint32_t>(subs) * C::kActSub);
-        for (int u = 0; u < subs; ++u) tma_load_2d(s_act + s * C::kActBytes + u * C::kActSub, &tmap_act, (it * kSub + u) * kBK, 0, &bar_xfull[s]);
-        if (++s == AS) { s = 0; if (it >= AS) ph ^= 1; }
-      }
-    }
-  } else if (warp == 1 || warp == 11) {
-    // ===================================== two MMA issuers (even / odd stages), accumulators zero-filled up front ==============
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_i8(kBM, NT, 1u, 1u);
-      const int first = (warp == 1) ? 0 : 1;
-      int sa = first % TA, sx = first % AS;
-      uint32_t pha = (first / TA) & 1, phx = (first / AS) & 1;
-      mbar_wait(bar_zero, 0);
-      tc_fence_after();
-      for (int it = first; it < n_kb; it += 2) {
-        mbar_wait(&bar_afull[sa], pha);
-        mbar_wait(&bar_xfull[sx], phx);
-        if (it == 0) QS_PROF(4);
-        tc_fence_after();
-        const int subs = subs_of(it);
-        for (int u = 0; u < subs; ++u) {
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + sx * C::kActBytes + u * C::kActSub));
-#pragma unroll
-          for (int t = 0; t < kBK / 32; ++t) {
-            const uint32_t a0 = tmem_base + 2 * NT + sa * C::kAStageCols + u * (kBK / 4) + t * 8;
-            umma_i8_ts(tmem_base, a0, bdesc + t * 2, idesc, 1u);
-            if (nb > 4) umma_i8_ts(tmem_base + NT, a0 + kSub * (kBK / 4), bdesc + t * 2, idesc, 1u);
-          }
-        }
-        umma_commit(&bar_aempty[sa]);
-        umma_commit(&bar_xempty[sx]);
-        sa += 2; if (sa >= TA) { sa -= TA; pha ^= 1; }
-        sx += 2; if (sx >= AS) { sx -= AS; phx ^= 1; }
-      }
-      if (n_kb > first) umma_commit(bar_dfull); else mbar_arrive(bar_dfull);
-      if (first == 0) QS_PROF(6);
-    }
-  } else if (warp >= 2 && warp <= 9) {
-    // ===================================== unpack + TMEM epilogue warps: 2..5 serve accumulator 0, 6..9 accumulator 1 ==========
-    const int quad = warp & 3;
-    const int h = (warp >= 6) ? 1 : 0;
-    const int epi_tid = quad * 32 + lane;
-    {
-      // zero-fill this quadrant of accumulator h (all MMAs accumulate)
-      const uint32_t tz = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + h * NT;
-#pragma unroll
-      for (int c = 0; c < NT; c += 8) {
-        tmem_st_16x128b_x2(tz + c, 0u, 0u, 0u, 0u);
-        tmem_st_16x128b_x2(tz + c + (16u << 16), 0u, 0u, 0u, 0u);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_zero);
-    }
-    {
-      int s = 0, ta = 0;
-      uint32_t ph = 0, pha = 0;
-      for (int it = 0; it < n_kb; ++it) {
-        mbar_wait(&bar_wfull[s], ph);
-        if (it >= TA) {
-          mbar_wait(&bar_aempty[ta], pha);
-          tc_fence_after();
-        }
-        const int subs = subs_of(it);
-        {
-          const int band = 4 * h + quad;
-          if (band < nb) {
-            for (int u = 0; u < subs; ++u) {
-              const uint8_t* wsrc = s_w + s * C::kWStage + u * (C::kBands * 2048) + band * 2048 + lane * 16;
-              const uint32_t tdst = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 2 * NT + ta * C::kAStageCols + h * (kSub * (kBK / 4)) + u * (kBK / 4);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const uint4 v = *reinterpret_cast<const uint4*>(wsrc + t * 512);
-                const uint32_t xl = v.x & 0x0F0F0F0Fu, xh = (v.x >> 4) & 0x0F0F0F0Fu;
-                const uint32_t yl = v.y & 0x0F0F0F0Fu, yh = (v.y >> 4) & 0x0F0F0F0Fu;
-                const uint32_t zl = v.z & 0x0F0F0F0Fu, zh = (v.z >> 4) & 0x0F0F0F0Fu;
-                const uint32_t wl = v.w & 0x0F0F0F0Fu, wh = (v.w >> 4) & 0x0F0F0F0Fu;
-                tmem_st_16x128b_x2(tdst + t * 8, xl, yl, zl, wl);
-                tmem_st_16x128b_x2(tdst + t * 8 + (16u << 16), xh, yh, zh, wh);
-              }
-            }
-          }
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bar_afull[ta]);
-          mbar_arrive(&bar_wempty[s]);
-        }
-        if (++s == WS) { s = 0; ph ^= 1; }
-        if (++ta == TA) { ta = 0; if (it >= TA) pha ^= 1; }
-      }
-    }
-    // ------------------------------------------ epilogue ------------------------------------------
-    pdl_wait();
-    if (h == 0) {
-      for (int j = epi_tid; j < NT; j += 128) {
-        const bool ok = j < p.M;
-        s_asc[j] = ok ? __half2float(p.ascales[j]) : 0.f;
-        s_asum[j] = ok ? __half2float(p.a_ssums[j]) : 0.f;
-      }
-    }
-    if (epi_tid == 0 && h == 0) QS_PROF(7);
-    mbar_wait(bar_dfull, 0);
-    tc_fence_after();
-    if (epi_tid == 0 && h == 0) QS_PROF(8);
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    if (4 * h < nb) {
-#pragma unroll 1
-      for (int c = 0; c < NT / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(trow + h * NT + c * 32, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s_red[(c * 32 + i) * (2 * kBM) + h * kBM + epi_tid] = static_cast<int32_t>(r[i]);
-      }
-    }
-    if (epi_tid == 0 && h == 0) QS_PROF(9);
-  } else {
-    pdl_wait();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  {
-    pdl_wait();
-    if (threadIdx.x == 0) QS_PROF(10);
-    const float ws0 = __low2float(ws_h2), ws1 = __high2float(ws_h2), wz0 = __low2float(wz_h2), wz1 = __high2float(wz_h2);
-    const int tok_end = min(NT, p.M);
-    const int tpar = static_cast<int>(threadIdx.x) >> 7;  // 0 / 1: even / odd tokens
-    if (pr_ok && threadIdx.x < 256) {
-      auto finish = [&](int tok, int2 acc) {
-        const float as = s_asc[tok], asum = s_asum[tok];
-        const float o0 = epilogue_one<kModeW4Chn>(acc.x, ws0, wz0, as, asum);
-        const float o1 = epilogue_one<kModeW4Chn>(acc.y, ws1, wz1, as, asum);
-        __half* dst = p.out + static_cast<size_t>(tok) * p.N + n_ch;
-        *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(o0, o1);
-        if constexpr (ACC) *reinterpret_cast<int2*>(p.acc_out + (dst - p.out)) = acc;
-      };
-#pragma unroll 1
-      for (int t0 = tpar; t0 < NT; t0 += 16) {
-        int2 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const int2*>(s_red + (t0 + 2 * e) * (2 * kBM) + 2 * pr);
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (t0 + 2 * e < tok_end) finish(t0 + 2 * e, v[e]);
-      }
-    }
-    if (threadIdx.x == 0) QS_PROF(11);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) QS_PROF(12);
-  qs_trace(QS_K_GEMM, 2);
-  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -797,8 +513,42 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Tensor maps are pure functions of (address, shape, box): cuTensorMapEncodeTiled costs ~1 us of host time and an eager decode step issues
+// ~260 of them, so they are memoised (weights: one entry per layer and projection; activations: a handful of buffers).
+struct TmapKey {
+  const void* ptr; uint64_t a, b; uint32_t box, kind;
+  bool operator==(const TmapKey& o) const { return ptr == o.ptr && a == o.a && b == o.b && box == o.box && kind == o.kind; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.a + 0x7F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.b * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    return h ^ (static_cast<size_t>(k.box) << 7) ^ k.kind;
+  }
+};
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>& tmap_cache() {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> c;
+  return c;
+}
+std::mutex& tmap_mutex() { static std::mutex m; return m; }
+bool tmap_lookup(const TmapKey& k, CUtensorMap* m) {
+  std::lock_guard<std::mutex> g(tmap_mutex());
+  auto it = tmap_cache().find(k);
+  if (it == tmap_cache().end()) return false;
+  memcpy(m, &it->second, sizeof(CUtensorMap));
+  return true;
+}
+void tmap_store(const TmapKey& k, const CUtensorMap* m) {
+  std::lock_guard<std::mutex> g(tmap_mutex());
+  if (tmap_cache().size() > 16384) tmap_cache().clear();  // bounded: a serving loop cycles through a fixed set of buffers
+  memcpy(&tmap_cache()[k], m, sizeof(CUtensorMap));
+}
+
 // 2-D uint8 tensor [rows, cols] row-major, box {128 bytes, box_rows}, 128-byte swizzle, zero fill out of bounds
 int make_tmap_u8(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const TmapKey key{ptr, rows, cols, box_rows, 0u};
+  if (tmap_lookup(key, m)) return QS_OK;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(QS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
@@ -809,11 +559,14 @@ int make_tmap_u8(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(QS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%llu cols=%llu box_rows=%u", (int)r, ptr,
                                           (unsigned long long)rows, (unsigned long long)cols, box_rows);
+  tmap_store(key, m);
   return QS_OK;
 }
 
 // packed INT4 weights [N, K/2] seen as [N/32 bands][K*16 bytes] of uint64 elements; box = 4 bands x 2 KB (one 128-K block)
 int make_tmap_w4(CUtensorMap* m, const void* ptr, uint64_t N, uint64_t K, uint32_t box_bands = 4) {
+  const TmapKey key{ptr, N, K, box_bands, 1u};
+  if (tmap_lookup(key, m)) return QS_OK;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(QS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {K * 16 / 8, N / 32};
@@ -824,6 +577,7 @@ int make_tmap_w4(CUtensorMap* m, const void* ptr, uint64_t N, uint64_t K, uint32
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(QS_ERR_CUDA, "cuTensorMapEncodeTiled(w4) failed (%d): ptr=%p N=%llu K=%llu", (int)r, ptr, (unsigned long long)N,
                                           (unsigned long long)K);
+  tmap_store(key, m);
   return QS_OK;
 }
 
@@ -895,54 +649,6 @@ int launch_gemm(const GemmArgs& a) {
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, tm_act, tm_w, p), "gemm launch");
 }
 
-// wide per-channel layers at decode size: one CTA per SM over a balanced partition of the 32-channel bands
-template <int NT>
-int launch_gemm_wide(const GemmArgs& a) {
-  constexpr int WS = 4, AS = (NT == 64 ? 4 : 6);
-  using C = WideCfg<NT, WS, AS>;
-  GemmParams p{};
-  p.wscales = static_cast<const __half*>(a.wscales);
-  p.w_szs = static_cast<const __half*>(a.w_szs);
-  p.ascales = static_cast<const __half*>(a.ascales);
-  p.a_ssums = static_cast<const __half*>(a.a_ssums);
-  p.out = static_cast<__half*>(a.out);
-  p.acc_out = static_cast<int32_t*>(a.acc_out);
-  p.prof = static_cast<unsigned long long*>(a.prof);
-  p.w = static_cast<const uint8_t*>(a.weight);
-  p.M = a.M; p.N = a.N; p.K = a.K;
-  p.m_tiles = 1; p.split = 1;
-  const int bands = a.N / 32;
-  int grid = num_sms();
-  if (grid > bands) grid = bands;
-  CUtensorMap tm_act, tm_lo, tm_hi;
-  int rc = make_tmap_u8(&tm_act, a.act, a.M, a.K, NT);
-  if (rc) return rc;
-  const int nb_lo = bands / grid;
-  rc = make_tmap_w4(&tm_lo, a.weight, a.N, a.K, nb_lo);
-  if (rc) return rc;
-  rc = make_tmap_w4(&tm_hi, a.weight, a.N, a.K, nb_lo + (bands % grid ? 1 : 0));
-  if (rc) return rc;
-  auto kern = a.acc_out ? gemm_wide_kernel<NT, WS, AS, true> : gemm_wide_kernel<NT, WS, AS, false>;
-  static bool attr_set[2][kMaxDevices] = {};
-  bool& done = attr_set[a.acc_out ? 1 : 0][device_ordinal()];
-  if (!done) {
-    rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "cudaFuncSetAttribute(gemm wide smem)");
-    if (rc) return rc;
-    done = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kWideThreads);
-  cfg.dynamicSmemBytes = C::kSmemBytes;
-  cfg.stream = static_cast<cudaStream_t>(a.stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, kern, tm_act, tm_lo, tm_hi, p), "gemm (wide) launch");
-}
-
 template <int MODE>
 int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
@@ -952,15 +658,7 @@ int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.force_split == 0 || a.force_split == 1 || a.force_split == 2 || a.force_split == 4 || a.force_split == 8, "gemm: split must be 1, 2, 4 or 8");
   // weight-ring depths (256-K stages) chosen so that NT <= 128 fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns)
   constexpr bool w8 = (MODE == kModeW8), grp = (MODE == kModeW4Grp);
-  QS_REQUIRE(a.force_nt == -1 || a.force_nt == 0 || a.force_nt == 32 || a.force_nt == 64 || a.force_nt == 128 || a.force_nt == 256, "gemm: tile tokens must be 32, 64, 128 or 256");
-  if constexpr (MODE == kModeW4Chn) {
-    // wide layers at decode size: balanced band partition, one CTA per SM.  Bit-exact but, as measured in round 1, slower
-    // than two tiled CTAs per SM (20.1 vs 15.7 us for gate_up: its single MMA / TMEM-ring chain per SM paces the weight
-    // stream, profiles/r01_notes.md), so it is only taken on request: qs_gemm_force_tile_tokens(-1).
-    const int sms = num_sms();
-    if (a.force_nt == -1 && a.force_split == 0 && a.M <= 64 && a.N / kBM > sms && a.N / 32 <= 8 * sms)
-      return a.M <= 32 ? launch_gemm_wide<32>(a) : launch_gemm_wide<64>(a);
-  }
+  QS_REQUIRE(a.force_nt == 0 || a.force_nt == 32 || a.force_nt == 64 || a.force_nt == 128 || a.force_nt == 256, "gemm: tile tokens must be 32, 64, 128 or 256");
   int nt = a.force_nt > 0 ? a.force_nt : 0;
   if (nt == 0) {
     nt = a.M <= 32 ? 32 : a.M <= 64 ? 64 : a.M <= 128 ? 128 : 256;

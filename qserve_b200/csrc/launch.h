@@ -52,6 +52,8 @@ int argmax_rows(void* out_i64, const void* logits_f16, int rows, int vocab, void
 int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int d, void* stream);
 int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void* delta, const void* gamma, void* input_sum, void* scaling, float eps,
                         int tokens, int hidden, void* stream);
+int add_layernorm_quant_peer(void* out_q, void* hidden_out, const void* x, const void* const* delta_ptrs, void* const* flag_ptrs, void* state, int world,
+                             int rank, int phase, const void* gamma, void* input_sum, void* scaling, float eps, int tokens, int hidden, void* stream);
 int gelu(void* out, const void* in, int tokens, int d, int fast, void* stream);
 int dequant_add_residual(void* out, const void* in_i32, const void* residual, const void* scale_vec, float scale, int tokens, int hidden,
                          void* stream);
@@ -82,10 +84,6 @@ struct DecodeAttnArgs {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   void* stream = nullptr;
-  // optional: static byte ranges (the weights of the GEMMs that follow) the kernel prefetches into L2 while it streams the KV pages:
-  // the attention loop is ALU-bound at ~45 % of the HBM bandwidth, the spare bandwidth pre-stages the next layers' weights
-  const void* pf_ptr[2] = {nullptr, nullptr};
-  unsigned long long pf_bytes[2] = {0, 0};
 };
 int decode_attention(const DecodeAttnArgs& a);
 size_t attention_workspace_bytes(int batch, int num_heads, int head_dim, int max_splits);

@@ -94,11 +94,14 @@ class _Linear:
 class DecodeRunner:
     def __init__(self, model: str = "llama-3-8b", precision: str = "w4a8kv4", batch: int = 64, ctx: int = 1024,
                  device: Optional[torch.device] = None, tp_rank: int = 0, tp_size: int = 1, seed: int = 0, layers: Optional[int] = None,
-                 process_group=None, fused: bool = True, ops: Optional[OpSet] = None, tp_exact: bool = False, l2_prefetch: bool = False):
+                 process_group=None, fused: bool = True, ops: Optional[OpSet] = None, tp_exact: bool = False, tp_peer: bool = False):
         assert precision in PRECISIONS, precision
         self.ops = ops = ops or DEFAULT_OPS
         self.tp_exact = tp_exact
-        self.l2_prefetch = l2_prefetch  # the attention kernel pre-stages the following GEMMs' weights into L2 (fused path only)
+        # tensor parallel, fused path: the all-reduce of the row-parallel GEMM outputs is folded into the following add+norm+quant kernel
+        # (peer loads over NVLink symmetric memory) instead of an NCCL call
+        self.tp_peer = tp_peer and tp_size > 1
+        assert not (self.tp_peer and not fused), "tp_peer needs the fused path"
         assert ops is DEFAULT_OPS or not fused, "the fused extensions exist only in this repo's library"
         self.cfg = cfg = MODELS[model]
         self.precision, self.batch, self.ctx = precision, batch, ctx
@@ -172,6 +175,9 @@ class DecodeRunner:
         self.q_sum = torch.empty(M, dtype=torch.half, device=dev)
         self.q_amax = torch.empty(M, dtype=torch.float32, device=dev)  # TP parity mode: per-token amax, max-all-reduced
         self.mlp_act = torch.empty((M, self.Iloc), dtype=torch.half, device=dev)  # reference: fresh torch.empty per call (activation.py:26)
+        self.peer = None
+        if self.tp_peer:
+            self.peer = _ext.PeerContext(M, H, dev, process_group if process_group is not None else torch.distributed.group.WORLD)
         self.tokens_in = torch.zeros(M, dtype=torch.int64, device=dev)
         self.tokens_out = torch.zeros(M, dtype=torch.int64, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -266,15 +272,17 @@ class DecodeRunner:
         for li, ly in enumerate(self.layers):
             exact = self.tp_size > 1 and self.tp_exact
             ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
-            if self.l2_prefetch and self.wmode != "w8":
-                _ext.attention_prefetch_next(ly["o"].qweight, ly["gate_up"].qweight)
             if exact:
                 self._quant(self.q_attn, self._attention(li))
             else:
                 self._attention_quant(li, qsum)
-            ly["o"](self.q_attn, self.q_scale, self.q_sum, self.out_buf)
-            self._allreduce(self.out_buf)
-            _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, ly["ln2"], qsum, self.q_scale, cfg.eps)
+            if self.tp_peer:
+                ly["o"](self.q_attn, self.q_scale, self.q_sum, self.peer.partial[0])
+                _ext.add_rms_norm_general_peer(self.q_hidden, nxt, hidden, self.peer, 0, ly["ln2"], qsum, self.q_scale, cfg.eps)
+            else:
+                ly["o"](self.q_attn, self.q_scale, self.q_sum, self.out_buf)
+                self._allreduce(self.out_buf)
+                _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, ly["ln2"], qsum, self.q_scale, cfg.eps)
             hidden, nxt = nxt, hidden
             ly["gate_up"](self.q_hidden, self.q_scale, self.q_sum, self.gate_up_buf)
             if exact:
@@ -282,10 +290,19 @@ class DecodeRunner:
                 self._quant(self.q_mlp, self.mlp_act)
             else:
                 _ext.silu_and_mul_quant(self.q_mlp, self.gate_up_buf, qsum, self.q_scale)
-            ly["down"](self.q_mlp, self.q_scale, self.q_sum, self.out_buf)
-            self._allreduce(self.out_buf)
+            if self.tp_peer:
+                ly["down"](self.q_mlp, self.q_scale, self.q_sum, self.peer.partial[1])
+            else:
+                ly["down"](self.q_mlp, self.q_scale, self.q_sum, self.out_buf)
+                self._allreduce(self.out_buf)
             n += 11 if exact else 7
-            if li + 1 < len(self.layers):
+            if self.tp_peer:
+                # the last layer has no following norm: the same kernel delivers hidden + sum(partials) (its quantised output is not used)
+                gam = self.layers[li + 1]["ln1"] if li + 1 < len(self.layers) else ly["ln1"]
+                _ext.add_rms_norm_general_peer(self.q_hidden, nxt, hidden, self.peer, 1, gam, qsum, self.q_scale, cfg.eps)
+                hidden, nxt = nxt, hidden
+                n += 1
+            elif li + 1 < len(self.layers):
                 _ext.add_rms_norm_general(self.q_hidden, nxt, hidden, self.out_buf, self.layers[li + 1]["ln1"], qsum, self.q_scale, cfg.eps)
                 hidden, nxt = nxt, hidden
                 n += 1

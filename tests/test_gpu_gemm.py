@@ -177,30 +177,20 @@ def test_baseline_config_shapes_bit_exact(dev, mode, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 28672, 4096), (16, 19072, 384), (33, 37888, 256), (1, 20480, 128), (64, 24576, 1152)])
-def test_wide_band_partition_kernel_bit_exact(dev, M, N, K):
-    """The band-partitioned two-accumulator kernel for layers with more 128-channel tiles than SMs (selected with
-    qs_gemm_force_tile_tokens(-1)): bit-exact and identical to the tiled kernel, including K % 256 == 128 and uneven band counts."""
+def test_wide_layers_bit_exact(dev, M, N, K):
+    """Layers with more 128-channel tiles than SMs (two CTAs per SM, several waves), including K % 256 == 128: bit-exact."""
     import qserve_backend.qgemm_w4a8_per_chn as op
-    from qserve_b200._lib import lib
     rng = np.random.default_rng(M + N + K)
     q, qw, s1, s1z = w4a8.synth_per_channel(rng, N, K)
     aq, sa, asum = _acts(rng, M, K)
     out_o, acc_o = w4a8.gemm_w4a8_per_chn(aq, qw, s1, sa, s1z, asum, return_acc=True)
     args = [to_dev(a, dev) for a in (aq, qw, s1, sa, s1z, asum)]
-    res = []
-    for forced in (-1, 0):
-        lib.qs_gemm_force_tile_tokens(forced)
-        try:
-            out = torch.full((M, N), float("nan"), dtype=torch.half, device=dev)
-            acc = torch.zeros((M, N), dtype=torch.int32, device=dev)
-            op.gemm_forward_cuda(*args, out, _acc_out=acc)
-            torch.cuda.synchronize()
-        finally:
-            lib.qs_gemm_force_tile_tokens(0)
-        res.append((np_of(acc), np_of(out)))
-    for acc_g, out_g in res:
-        assert np.array_equal(acc_g, acc_o)
-        assert np.array_equal(bits16(out_g), bits16(out_o))
+    out = torch.full((M, N), float("nan"), dtype=torch.half, device=dev)
+    acc = torch.zeros((M, N), dtype=torch.int32, device=dev)
+    op.gemm_forward_cuda(*args, out, _acc_out=acc)
+    torch.cuda.synchronize()
+    assert np.array_equal(np_of(acc), acc_o)
+    assert np.array_equal(bits16(np_of(out)), bits16(out_o))
 
 
 def test_linearity_property_full_size(dev):

@@ -91,6 +91,26 @@ def _worker(rank, world, port, precision, q):
             ls = shard._forward_reference(tokens, return_logits=True).float()
             ls_fused = shard._forward_fused(tokens, return_logits=True).float()
         torch.cuda.synchronize()
+        # (4) throughput modes: local amax inside the fused kernels, all-reduce by NCCL vs fused into the add+norm+quant kernel over peer memory
+        fast_nccl = DecodeRunner("tiny", precision, batch=8, ctx=130, device=dev, seed=3, tp_rank=rank, tp_size=world)
+        fast_peer = DecodeRunner("tiny", precision, batch=8, ctx=130, device=dev, seed=3, tp_rank=rank, tp_size=world, tp_peer=True)
+        fast_nccl.load_shard_of(full); fast_peer.load_shard_of(full)
+        with torch.no_grad():
+            ln = fast_nccl._forward_fused(tokens, return_logits=True).float()
+            lp = fast_peer._forward_fused(tokens, return_logits=True).float()
+            lp2 = fast_peer._forward_fused(tokens, return_logits=True).float()   # second launch: epochs advance, same result
+        torch.cuda.synchronize()
+        gathered = [torch.empty_like(lp) for _ in range(world)]
+        dist.all_gather(gathered, lp)
+        res["peer_ranks_bit_identical"] = bool(all(torch.equal(g_, gathered[0]) for g_ in gathered))  # rank-ordered fp32 sums
+        res["peer_repeatable"] = bool(torch.equal(lp, lp2))
+        res["peer_vs_nccl_rel"] = float((lp - ln).norm() / ln.norm())
+        res["peer_vs_full_rel"] = float((lp - lf).norm() / lf.norm())
+        fast_peer.capture()   # and the peer protocol survives CUDA-graph capture / replay (device-side epochs)
+        fast_peer.tokens_in.copy_(tokens)
+        fast_peer.step(); fast_peer.step()
+        torch.cuda.synchronize()
+        res["peer_graph_tokens_match"] = bool(torch.equal(fast_peer.tokens_out, lp.argmax(-1)))
         res["logits_rel"] = float((ls - lf).norm() / lf.norm())
         res["fused_equals_unfused_tp"] = bool(torch.equal(ls_fused, ls))  # the second pass re-appends the same token: same cache
         top2 = lf.topk(2, dim=-1).values
@@ -130,3 +150,5 @@ def test_tp2_parity_rule_nccl(precision):
         assert res["logits_rel"] < 2e-2, res["logits_rel"]
         assert res["tokens_equal_where_margin"]
         assert res["fused_equals_unfused_tp"]
+        assert res["peer_ranks_bit_identical"] and res["peer_repeatable"] and res["peer_graph_tokens_match"]
+        assert res["peer_vs_nccl_rel"] < 5e-3 and res["peer_vs_full_rel"] < 5e-2, (res["peer_vs_nccl_rel"], res["peer_vs_full_rel"])
