@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-tp", action="store_true", help="skip the Qwen1.5-72B tensor-parallel record")
     ap.add_argument("--tp-model", default="qwen1.5-72b")
     ap.add_argument("--tp-layers", type=int, default=None, help="debug only")
+    ap.add_argument("--tp-only", action="store_true", help="print only the tensor-parallel record (tuning runs)")
     ap.add_argument("--tp-allreduce", default="peer", choices=["peer", "nccl"], help="TP record: all-reduce fused into add+norm+quant over peer memory, or NCCL")
     ap.add_argument("--tp-exact", action="store_true", help="TP record with the bit-exact parity rule (global per-token amax) instead of the throughput mode")
     ap.add_argument("--no-pdl", action="store_true")
@@ -617,6 +618,16 @@ def main():
 
     backend.set_pdl(not args.no_pdl)
     cfg = model_cfg(args.model)
+    if args.tp_only:
+        with torch.no_grad():
+            rec = tp_block(args, rank, world, dev, peaks()[0])
+        if rank == 0:
+            print(json.dumps({"tp": rec}), flush=True)
+        sys.stdout.flush()
+        if world > 1:
+            dist.barrier()
+            os._exit(0)
+        return
     run = DecodeRunner(args.model, args.precision, args.batch, args.ctx, dev, seed=rank, layers=args.layers, fused=not args.no_fused)
     hbm_gbs, peak_src = peaks()
 
@@ -642,6 +653,12 @@ def main():
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             step()
+        if os.environ.get("QS_PROFILE_STEP"):  # ncu --profile-from-start off: exactly one eager step between profiler start / stop
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            run.tokens_out.copy_(run.forward(run.tokens_in))
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         # ---- device-resident timing: exactly K steps, CUDA events, max over ranks -------------------------
         barrier()
         with ClockSampler(local_rank) as clk:
