@@ -708,6 +708,8 @@ def main():
     torch.cuda.empty_cache()
     tp_rec = None
     if not args.no_tp and (args.model, args.precision) == ("llama-3-8b", "w4a8kv4"):
+        if world > 1:
+            dist.barrier()  # rank 0 has just spent seconds on the kernel table: enter the collective phase together
         try:
             with torch.no_grad():
                 tp_rec = tp_block(args, rank, world, dev, hbm_gbs)

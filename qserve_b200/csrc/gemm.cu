@@ -140,6 +140,9 @@ __device__ __forceinline__ float int2float_rn_noxu(int32_t v) {
   return __fmaf_rn(fhi, 65536.f, flo);
 }
 
+template <int V>
+struct IntTag { static constexpr int value = V; };
+
 template <int MODE>
 __device__ __forceinline__ float epilogue_one(int32_t acc, float ws, float wsz, float as, float asum) {
   // IEEE fp32, reference source order, no FMA contraction (bit-exact against oracle/w4a8.py)
@@ -471,20 +474,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
       const int cps = kBM / S;
       const int32_t* rx = reinterpret_cast<const int32_t*>(smem + C::kOffRx);
       const int prl = tid % npairs;  // channel pair inside this CTA's slice
-      const int tpt = NT / (4 * S);  // tokens of this thread
-#pragma unroll 1
-      for (int i = 0; i < tpt; ++i) {
-        const int tok = tok0 + i * tstep;
-        int2 acc = make_int2(0, 0);
+      // tokens of this thread: NT / (4 S); S is a launch constant of the cluster: specialise so that all S x tokens shared-memory loads of a
+      // thread are in flight together (the rolled loop serialised 4 dependent LDS -> add -> convert -> scale -> store chains)
+      auto reduce_rows = [&](auto s_tag) {
+        constexpr int SS = decltype(s_tag)::value;
+        constexpr int TPT = NT / (4 * SS) > 0 ? NT / (4 * SS) : 1;
+        int2 v[TPT][SS];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          if (r < S) {
-            const int2 v = *reinterpret_cast<const int2*>(rx + (r * NT + tok) * cps + 2 * prl);
-            acc.x += v.x; acc.y += v.y;
-          }
+        for (int i = 0; i < TPT; ++i) {
+          const int tok = tok0 + i * tstep;
+#pragma unroll
+          for (int r = 0; r < SS; ++r)
+            v[i][r] = (tok < NT) ? *reinterpret_cast<const int2*>(rx + (r * NT + tok) * cps + 2 * prl) : make_int2(0, 0);
         }
-        if (tok < tok_end) finish(tok, acc, optr + i * ostep);
-      }
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+          const int tok = tok0 + i * tstep;
+          int2 acc = v[i][0];
+#pragma unroll
+          for (int r = 1; r < SS; ++r) { acc.x += v[i][r].x; acc.y += v[i][r].y; }
+          if (tok < tok_end) finish(tok, acc, optr + i * ostep);
+        }
+      };
+      if (S == 2) reduce_rows(IntTag<2>{});
+      else if (S == 4) reduce_rows(IntTag<4>{});
+      else reduce_rows(IntTag<8>{});
     }
     if (tid == 0) QS_PROF(11);
   }
@@ -658,15 +672,16 @@ int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.force_split == 0 || a.force_split == 1 || a.force_split == 2 || a.force_split == 4 || a.force_split == 8, "gemm: split must be 1, 2, 4 or 8");
   // weight-ring depths (256-K stages) chosen so that NT <= 128 fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns)
   constexpr bool w8 = (MODE == kModeW8), grp = (MODE == kModeW4Grp);
-  QS_REQUIRE(a.force_nt == 0 || a.force_nt == 32 || a.force_nt == 64 || a.force_nt == 128 || a.force_nt == 256, "gemm: tile tokens must be 32, 64, 128 or 256");
+  QS_REQUIRE(a.force_nt == 0 || a.force_nt == 32 || a.force_nt == 64 || a.force_nt == 128, "gemm: tile tokens must be 32, 64 or 128");
   int nt = a.force_nt > 0 ? a.force_nt : 0;
   if (nt == 0) {
-    nt = a.M <= 32 ? 32 : a.M <= 64 ? 64 : a.M <= 128 ? 128 : 256;
+    // prefill-sized M: 128-token tiles with TWO co-resident CTAs per SM beat the 256-token tile (one CTA per SM) by 14-15 % (M = 1024: 2071 vs
+    // 1796 TOP/s, M = 4096: 2388 vs 2100, profiles/r02_notes.md): a tile's setup, pipeline fill and epilogue hide behind the sibling's main loop
+    nt = a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
   }
   if (nt == 32) return launch_gemm<MODE, 32, (w8 ? 2 : grp ? 4 : 5), 4>(a);
   if (nt == 64) return launch_gemm<MODE, 64, (w8 ? 2 : grp ? 3 : 4), 3>(a);
-  if (nt == 128) return launch_gemm<MODE, 128, (w8 ? 4 : 2), 2>(a);
-  return launch_gemm<MODE, 256, (w8 ? 2 : 5), 2>(a);
+  return launch_gemm<MODE, 128, (w8 ? 4 : 2), 2>(a);
 }
 
 }  // namespace

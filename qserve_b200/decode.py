@@ -94,10 +94,11 @@ class _Linear:
 class DecodeRunner:
     def __init__(self, model: str = "llama-3-8b", precision: str = "w4a8kv4", batch: int = 64, ctx: int = 1024,
                  device: Optional[torch.device] = None, tp_rank: int = 0, tp_size: int = 1, seed: int = 0, layers: Optional[int] = None,
-                 process_group=None, fused: bool = True, ops: Optional[OpSet] = None, tp_exact: bool = False, tp_peer: bool = False):
+                 process_group=None, fused: bool = True, ops: Optional[OpSet] = None, tp_exact: bool = False, tp_peer: bool = False, no_comm: bool = False):
         assert precision in PRECISIONS, precision
         self.ops = ops = ops or DEFAULT_OPS
         self.tp_exact = tp_exact
+        self.no_comm = no_comm  # debugging: run one rank's shard of a tensor-parallel model without the collectives (sanitizer / profiler runs)
         # tensor parallel, fused path: the all-reduce of the row-parallel GEMM outputs is folded into the following add+norm+quant kernel
         # (peer loads over NVLink symmetric memory) instead of an NCCL call
         self.tp_peer = tp_peer and tp_size > 1
@@ -195,7 +196,8 @@ class DecodeRunner:
         if self.tp_size > 1 and self.tp_exact:
             # same per-token scale on all ranks (global amax), local-K-shard activation sum
             _ext.row_absmax(self.q_amax, x)
-            torch.distributed.all_reduce(self.q_amax, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            if not self.no_comm:
+                torch.distributed.all_reduce(self.q_amax, op=torch.distributed.ReduceOp.MAX, group=self.pg)
             _ext.invoke_quant_given_amax(out_q, x, self.q_amax, self.q_sum if self.act_sum else None, self.q_scale)
         elif self.act_sum:  # llama_w4a8_unpad.py:177-183
             self.ops.fused_kernels.invoke_quant_fuse_sum(out_q, x, self.q_sum, self.q_scale)
@@ -203,7 +205,7 @@ class DecodeRunner:
             self.ops.fused_kernels.invoke_quant(out_q, x, self.q_scale)
 
     def _allreduce(self, t):
-        if self.tp_size > 1:
+        if self.tp_size > 1 and not self.no_comm:
             torch.distributed.all_reduce(t, group=self.pg)
 
     def forward(self, tokens: torch.Tensor) -> torch.Tensor:

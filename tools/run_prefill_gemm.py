@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import qserve_backend.qgemm_w4a8_per_chn as op  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+if os.environ.get("QS_FORCE_NT"):  # tile-size A/B: tokens per tile (32 / 64 / 128 / 256)
+    from qserve_b200._lib import lib
+    lib.qs_gemm_force_tile_tokens(int(os.environ["QS_FORCE_NT"]))
 N, K = 28672, 4096
 dev = torch.device("cuda:0")
 g = torch.Generator(device="cpu").manual_seed(0)
