@@ -116,7 +116,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // fast path: the non-blocking probe (the potentially-blocking try_wait costs ~200 cycles even on a completed phase)
   if (mbar_test_wait(bar, parity)) return;
   // bounded wait: a protocol bug must surface as a trapped launch (reported by the host), never as a hung GPU.  The bound is wall-clock
-  // (30 s of %globaltimer), not a spin count: under tensor parallelism a kernel legitimately waits -- through its dependency chain -- for a
+  // (10 s of %globaltimer), not a spin count: under tensor parallelism a kernel legitimately waits -- through its dependency chain -- for a
   // peer rank that may be late by a host scheduling quantum or a whole warm-up phase.
   uint32_t spins = 0;
   unsigned long long t0 = 0;
@@ -125,7 +125,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
       if (t0 == 0) t0 = t;
-      if (t - t0 > 30000000000ull) {
+      if (t - t0 > 10000000000ull) {
         printf("qserve_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
         __trap();
       }

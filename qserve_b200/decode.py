@@ -98,6 +98,8 @@ class DecodeRunner:
         assert precision in PRECISIONS, precision
         self.ops = ops = ops or DEFAULT_OPS
         self.tp_exact = tp_exact
+        import os as _os
+        self.fuse_attn_quant = _os.environ.get("QS_UNFUSED_ATTN_QUANT") is None  # A/B hook: attention + separate per-token quant kernel
         self.no_comm = no_comm  # debugging: run one rank's shard of a tensor-parallel model without the collectives (sanitizer / profiler runs)
         # tensor parallel, fused path: the all-reduce of the row-parallel GEMM outputs is folded into the following add+norm+quant kernel
         # (peer loads over NVLink symmetric memory) instead of an NCCL call
@@ -274,7 +276,7 @@ class DecodeRunner:
         for li, ly in enumerate(self.layers):
             exact = self.tp_size > 1 and self.tp_exact
             ly["qkv"](self.q_hidden, self.q_scale, self.q_sum, self.qkv_buf)
-            if exact:
+            if exact or not self.fuse_attn_quant:
                 self._quant(self.q_attn, self._attention(li))
             else:
                 self._attention_quant(li, qsum)
