@@ -461,6 +461,88 @@ __global__ void __launch_bounds__(kSiluQuantThreads) silu_mul_quant_kernel(int8_
   if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 
+// Register-resident form of silu_mul_quant_kernel for slices of at most 2 x 256 vectors per CTA (every benchmark shape): the activation
+// stays in registers, the two block reductions need one barrier each, and the cluster exchange is PUSH based -- every CTA stores its
+// (amax, sum) into all peers' tables before ONE cluster barrier and reads only its own shared memory afterwards, so no trailing barrier keeps
+// the CTAs alive.  Same arithmetic (exact sums, max) as the kernel above: bit-identical results.
+template <int CHS>
+__global__ void __launch_bounds__(kSiluQuantThreads) silu_mul_quant_fast_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
+                                                                           __half* __restrict__ input_sum, __half* __restrict__ scale, int d, int csize) {
+  __shared__ float red[32];
+  __shared__ long long red_ll[32];
+  __shared__ __align__(16) long long s_rx[8][2];  // [sender]: bits of its amax, its fixed-point sum
+  const int row = blockIdx.x / csize;
+  const int rank = blockIdx.x - row * csize;
+  const int dl = d / csize;
+  const int nvec = dl / 8;
+  qs_trace(QS_K_SILUQ, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  qs_trace(QS_K_SILUQ, 1);
+  const uint4* gx = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + static_cast<size_t>(rank) * dl);
+  const uint4* gy = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * 2 * d + d + static_cast<size_t>(rank) * dl);
+  uint4 xin[CHS], yin[CHS];
+#pragma unroll
+  for (int c = 0; c < CHS; ++c) {  // all loads of the thread in flight together
+    const int i = threadIdx.x + c * kSiluQuantThreads;
+    if (i < nvec) { xin[c] = __ldg(gx + i); yin[c] = __ldg(gy + i); }
+  }
+  float act[CHS][8];
+  float amax = 0.f;
+  long long s = 0;
+#pragma unroll
+  for (int c = 0; c < CHS; ++c) {
+    if (threadIdx.x + c * kSiluQuantThreads < nvec) {
+      const __half* xh = reinterpret_cast<const __half*>(&xin[c]);
+      const __half* yh = reinterpret_cast<const __half*>(&yin[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = __half2float(__hmul(silu_h_fused(xh[j]), yh[j]));
+        act[c][j] = f;
+        if (input_sum) s += fx_of_half(f);
+        amax = fmaxf(amax, fabsf(f));
+      }
+    }
+  }
+  // one barrier for both block reductions: warp partials of amax and of the exact sum are published together
+  amax = warp_reduce(amax, OpMax());
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[w] = amax; red_ll[w] = s; }
+  __syncthreads();
+  amax = (l < (kSiluQuantThreads >> 5)) ? red[l] : 0.f;
+  amax = warp_reduce(amax, OpMax());
+  long long total = (l < (kSiluQuantThreads >> 5)) ? red_ll[l] : 0ll;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+  if (csize > 1) {
+    if (threadIdx.x < csize) {  // thread r pushes this CTA's pair into CTA r's table
+      uint32_t peer;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(&s_rx[rank][0]))), "r"(threadIdx.x));
+      asm volatile("st.shared::cluster.v2.s64 [%0], {%1, %2};" ::"r"(peer), "l"(static_cast<long long>(__float_as_int(amax))), "l"(total) : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    amax = 0.f;
+    total = 0;
+    for (int r = 0; r < csize; ++r) {
+      amax = fmaxf(amax, __int_as_float(static_cast<int>(s_rx[r][0])));
+      total += s_rx[r][1];
+    }
+  }
+  if (rank == 0 && threadIdx.x == 0) {
+    scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+    if (input_sum) input_sum[row] = __float2half_rn(fx_to_float(total));
+  }
+  const float qs_ = __fdiv_rn(127.f, amax);
+  int8_t* orow = out + static_cast<size_t>(row) * d + static_cast<size_t>(rank) * dl;
+#pragma unroll
+  for (int c = 0; c < CHS; ++c) {
+    const int i = threadIdx.x + c * kSiluQuantThreads;
+    if (i < nvec) store_q8(orow, i, act[c], qs_);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Q1: invoke_quant / invoke_quant_fuse_sum (per-token)   fused_kernels.cu:52-137
 // ------------------------------------------------------------------------------------------------
@@ -801,6 +883,199 @@ __global__ void __launch_bounds__(kThreads) argmax_rows_kernel(long long* __rest
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");  // peers' smem stays valid
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident fast path of N1 and of its fused forms (per-token quantisation, H <= 8 * kThreads * CH, CH <= 2: every model of the
+// benchmark).  ONE body serves rms_norm_general[_fuse_sum], add_rms_norm_general and its peer (fused all-reduce) form, so the fused and the
+// unfused ops are bit-identical by construction.  Against the shared-memory kernels above it keeps the row in registers (no re-reads) and needs
+// 4 block barriers instead of 9: a decode-size row op is a pure latency chain (profiles/r02_notes.md), every barrier and round trip counts.
+// Arithmetic and reduction trees are those of layernorm_quant_kernel (same thread -> element map, same shuffle order).
+// ------------------------------------------------------------------------------------------------
+template <typename Op>
+__device__ __forceinline__ float block_reduce_1sync(float v, float* buf, Op op, float identity) {
+  // `buf` must not be the buffer of the immediately preceding call (the callers alternate two buffers): then one barrier suffices
+  v = warp_reduce(v, op);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) buf[w] = v;
+  __syncthreads();
+  float r = (l < (blockDim.x >> 5)) ? buf[l] : identity;
+  return warp_reduce(r, op);
+}
+
+template <bool ADD, bool PEER, int CH>
+__global__ void __launch_bounds__(kThreads) norm_quant_fast_kernel(int8_t* __restrict__ out, __half* __restrict__ hidden_out, const __half* __restrict__ x,
+                                                                  const __half* __restrict__ delta, const __half* __restrict__ gamma,
+                                                                  __half* __restrict__ input_sum, __half* __restrict__ scaling, float eps, int H,
+                                                                  int ref_block, const PeerArgs peer) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  __half* sy = reinterpret_cast<__half*>(sm);  // half(y) row, only for the fused sum
+  __shared__ float red[2][32];
+  __shared__ long long red_ll[32];
+  const int row = blockIdx.x;
+  const int nvec = H / 8;
+  qs_trace(ADD ? QS_K_ADDNORM : QS_K_NORM, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  uint4 g[CH];  // gamma is a static weight: fetched before waiting for the producer of x / delta
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = threadIdx.x + c * kThreads;
+    g[c] = (i < nvec) ? __ldg(reinterpret_cast<const uint4*>(gamma) + i) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  pdl_wait();
+  qs_trace(ADD ? QS_K_ADDNORM : QS_K_NORM, 1);
+  uint32_t epoch = 0;
+  if constexpr (PEER) {
+    epoch = *reinterpret_cast<volatile uint32_t*>(peer.state + peer.phase) + 1u;
+    if (blockIdx.x == 0 && threadIdx.x < peer.world) st_release_sys(peer.flags[threadIdx.x] + peer.phase * 8 + peer.rank, epoch);
+    if (threadIdx.x < peer.world) {
+      const uint32_t* mine = peer.flags[peer.rank] + peer.phase * 8 + threadIdx.x;
+      unsigned spins = 0;
+      while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
+        __nanosleep(40);
+        if (++spins > (1u << 27)) {
+          printf("qserve_b200: peer all-reduce timed out (rank %d waits for rank %d, phase %d, epoch %u)\n", peer.rank, threadIdx.x, peer.phase, epoch);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- the row: this thread's chunks i = tid, tid + 512 (8 halves each), kept as packed fp16 in registers ----
+  uint4 xv[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = threadIdx.x + c * kThreads;
+    xv[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < nvec) {
+      const uint4 va = __ldg(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * H) + i);
+      if constexpr (ADD) {
+        uint4 vb;
+        if constexpr (PEER) {
+          uint4 pv[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r < peer.world) pv[r] = ld_peer_v4(reinterpret_cast<const uint4*>(peer.delta[r] + static_cast<size_t>(row) * H) + i);
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < peer.world) {
+              const __half2* hp = reinterpret_cast<const __half2*>(&pv[r]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(hp[j]);
+                acc[2 * j] = __fadd_rn(acc[2 * j], f.x);
+                acc[2 * j + 1] = __fadd_rn(acc[2 * j + 1], f.y);
+              }
+            }
+          }
+          __half2* hb2 = reinterpret_cast<__half2*>(&vb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hb2[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+        } else {
+          vb = __ldg(reinterpret_cast<const uint4*>(delta + static_cast<size_t>(row) * H) + i);
+        }
+        uint4 vo;
+        const __half2* ha = reinterpret_cast<const __half2*>(&va);
+        const __half2* hb = reinterpret_cast<const __half2*>(&vb);
+        __half2* ho2 = reinterpret_cast<__half2*>(&vo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // torch half add: float(a) + float(b), rounded once to fp16
+          const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
+          ho2[j] = __floats2half2_rn(__fadd_rn(fa.x, fb.x), __fadd_rn(fa.y, fb.y));
+        }
+        xv[c] = vo;
+        reinterpret_cast<uint4*>(hidden_out + static_cast<size_t>(row) * H)[i] = vo;
+      } else {
+        xv[c] = va;
+      }
+    }
+  }
+  // ---- mean, variance (two passes over registers; same per-thread order and reduction tree as the shared-memory kernels) ----
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (threadIdx.x + c * kThreads < nvec) {
+      const __half2* h = reinterpret_cast<const __half2*>(&xv[c]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s += f.x + f.y;
+      }
+    }
+  }
+  const float mean = __fdiv_rn(block_reduce_1sync(s, red[0], OpSum(), 0.f), static_cast<float>(H));
+  float vs = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (threadIdx.x + c * kThreads < nvec) {
+      const __half2* h = reinterpret_cast<const __half2*>(&xv[c]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        const float a = f.x - mean, b = f.y - mean;
+        vs += a * a + b * b;
+      }
+    }
+  }
+  const float var = block_reduce_1sync(vs, red[1], OpSum(), 0.f);
+  const float rstd = __frsqrt_rn(__fadd_rn(__fdiv_rn(var, static_cast<float>(H)), eps));
+  // ---- y, amax of half(y) (init 1e-6 in fp16), optional half(y) row for the reference-ordered fp16 sum ----
+  float amax = __half2float(__float2half_rn(1e-6f));
+  float y[CH][8];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = threadIdx.x + c * kThreads;
+    if (i < nvec) {
+      const __half* h = reinterpret_cast<const __half*>(&xv[c]);
+      const __half* gh = reinterpret_cast<const __half*>(&g[c]);
+      uint4 yv;
+      __half* yh = reinterpret_cast<__half*>(&yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[c][j] = __fmul_rn(__fmul_rn(__fsub_rn(__half2float(h[j]), mean), rstd), __half2float(gh[j]));
+        yh[j] = __float2half_rn(y[c][j]);
+        amax = fmaxf(amax, fabsf(__half2float(yh[j])));
+      }
+      if (input_sum) reinterpret_cast<uint4*>(sy)[i] = yv;
+    }
+  }
+  amax = block_reduce_1sync(amax, red[0], OpMax(), 0.f);  // its barrier also publishes sy
+  if (input_sum) {
+    // reference thread t (of ref_block threads) accumulates y_h[t], y_h[t+B], ... sequentially IN FP16 (layernorm_kernels.cu:275,286)
+    long long part = 0;
+    for (int t = threadIdx.x; t < ref_block; t += kThreads) {
+      __half acc = __float2half_rn(0.f);
+      for (int i = t; i < H; i += ref_block) acc = __hadd(acc, sy[i]);
+      part += fx_of_half(__half2float(acc));
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+    if ((threadIdx.x & 31) == 0) red_ll[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      long long r = (threadIdx.x < (kThreads >> 5)) ? red_ll[threadIdx.x] : 0ll;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+      if (threadIdx.x == 0) input_sum[row] = __float2half_rn(fx_to_float(r));
+    }
+  }
+  if (threadIdx.x == 0) scaling[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+  const float qs_ = __fdiv_rn(127.f, amax);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = threadIdx.x + c * kThreads;
+    if (i < nvec) store_q8(out + static_cast<size_t>(row) * H, i, y[c], qs_);  // quantises the UN-rounded fp32 y (:307-318)
+  }
+  if constexpr (PEER) {
+    if (threadIdx.x == 0) {
+      const uint32_t old = atomicAdd(peer.state + 2 + peer.phase, 1u);
+      if (old == gridDim.x - 1) {
+        peer.state[2 + peer.phase] = 0u;
+        *reinterpret_cast<volatile uint32_t*>(peer.state + peer.phase) = epoch;
+      }
+    }
+  }
+}
+
 template <typename Kern, typename... Args>
 int launch(Kern kern, dim3 grid, dim3 block, size_t smem, void* stream, const char* what, Args... args) {
   cudaLaunchConfig_t cfg{};
@@ -823,6 +1098,23 @@ int ensure_smem(Kern kern, size_t bytes, const char* what) {
   return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), what);
 }
 
+// fast path of the norm family: returns 1 if the shape is not eligible (caller falls back to the shared-memory kernels)
+template <bool ADD, bool PEER>
+int launch_norm_fast(void* out_q, void* hidden_out, const void* x, const void* delta, const void* gamma, void* input_sum, void* scaling, float eps,
+                     int tokens, int hidden, const PeerArgs& pa, void* stream, const char* what) {
+  const int nvec = hidden / 8;
+  if (nvec > 2 * kThreads) return 1;
+  int ref_block = hidden < 1024 ? hidden : 1024;
+  ref_block = 32 * ((ref_block + 31) / 32);  // layernorm_kernels.cu:433-436
+  const size_t smem = input_sum ? static_cast<size_t>(hidden) * 2 : 0;
+  auto go = [&](auto kern) {
+    return launch(kern, dim3(tokens), dim3(kThreads), smem, stream, what, static_cast<int8_t*>(out_q), static_cast<__half*>(hidden_out),
+                  static_cast<const __half*>(x), static_cast<const __half*>(delta), static_cast<const __half*>(gamma), static_cast<__half*>(input_sum),
+                  static_cast<__half*>(scaling), eps, hidden, ref_block, pa);
+  };
+  return nvec <= kThreads ? go(norm_quant_fast_kernel<ADD, PEER, 1>) : go(norm_quant_fast_kernel<ADD, PEER, 2>);
+}
+
 }  // namespace
 
 int elementwise_trace_install(void* buf, unsigned cap) { return qs_trace_install(buf, cap); }
@@ -842,6 +1134,10 @@ int layernorm_general_quant(void* out_q, const void* in, const void* gamma, void
   if (tokens == 0) return QS_OK;
   QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "rms_norm_general: hidden=%d must be a positive multiple of 8", hidden);
   QS_REQUIRE(per_token || input_sum == nullptr, "rms_norm_general_fuse_sum: per-tensor scaling with input_sum is not implemented by the reference either (layernorm_kernels.cu:490-494)");
+  if (per_token) {
+    const int fast = launch_norm_fast<false, false>(out_q, nullptr, in, nullptr, gamma, input_sum, scaling, eps, tokens, hidden, PeerArgs{}, stream, "rms_norm_general");
+    if (fast != 1) return fast;
+  }
   const size_t smem = static_cast<size_t>(hidden) * 2 * (input_sum ? 2 : 1);
   int rc = ensure_smem(layernorm_quant_kernel, smem, "rms_norm_general");
   if (rc) return rc;
@@ -933,9 +1229,13 @@ int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale
   // split a row over a cluster so that tokens * csize CTAs fill the machine (each CTA keeps >= 512 columns)
   int csize = 1;
   while (csize < 8 && tokens * csize < 2 * 148 && d % (csize * 2 * 8) == 0 && d / (csize * 2) >= 512) csize *= 2;
-  const size_t smem = static_cast<size_t>(d / csize) * 2;
-  int rc = ensure_smem(silu_mul_quant_kernel, smem, "silu_and_mul_quant");
-  if (rc) return rc;
+  const int nvec = d / csize / 8;
+  const bool fast = nvec <= 2 * kSiluQuantThreads;  // register-resident kernel (no dynamic shared memory)
+  const size_t smem = fast ? 0 : static_cast<size_t>(d / csize) * 2;
+  if (!fast) {
+    int rc = ensure_smem(silu_mul_quant_kernel, smem, "silu_and_mul_quant");
+    if (rc) return rc;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tokens * csize);
   cfg.blockDim = dim3(kSiluQuantThreads);
@@ -950,7 +1250,8 @@ int silu_and_mul_quant(void* out_q, const void* in, void* input_sum, void* scale
   attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return check_cuda(cudaLaunchKernelEx(&cfg, silu_mul_quant_kernel, static_cast<int8_t*>(out_q), static_cast<const __half*>(in),
+  auto kern = !fast ? silu_mul_quant_kernel : (nvec <= kSiluQuantThreads ? silu_mul_quant_fast_kernel<1> : silu_mul_quant_fast_kernel<2>);
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, static_cast<int8_t*>(out_q), static_cast<const __half*>(in),
                                        static_cast<__half*>(input_sum), static_cast<__half*>(scale), d, csize),
                     "silu_and_mul_quant");
 }
@@ -959,6 +1260,10 @@ int add_layernorm_quant(void* out_q, void* hidden_out, const void* x, const void
                         float eps, int tokens, int hidden, void* stream) {
   if (tokens == 0) return QS_OK;
   QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "add_rms_norm_general: hidden=%d must be a positive multiple of 8", hidden);
+  {
+    const int fast = launch_norm_fast<true, false>(out_q, hidden_out, x, delta, gamma, input_sum, scaling, eps, tokens, hidden, PeerArgs{}, stream, "add_rms_norm_general");
+    if (fast != 1) return fast;
+  }
   const size_t smem = static_cast<size_t>(hidden) * 2 * (input_sum ? 2 : 1);
   int rc = ensure_smem(add_layernorm_quant_kernel<false>, smem, "add_rms_norm_general");
   if (rc) return rc;
@@ -982,6 +1287,10 @@ int add_layernorm_quant_peer(void* out_q, void* hidden_out, const void* x, const
   }
   pa.state = static_cast<uint32_t*>(state);
   pa.world = world; pa.rank = rank; pa.phase = phase;
+  {
+    const int fast = launch_norm_fast<true, true>(out_q, hidden_out, x, nullptr, gamma, input_sum, scaling, eps, tokens, hidden, pa, stream, "add_rms_norm_general_peer");
+    if (fast != 1) return fast;
+  }
   const size_t smem = static_cast<size_t>(hidden) * 2 * (input_sum ? 2 : 1);
   int rc = ensure_smem(add_layernorm_quant_kernel<true>, smem, "add_rms_norm_general_peer");
   if (rc) return rc;

@@ -98,8 +98,7 @@ class DecodeRunner:
         assert precision in PRECISIONS, precision
         self.ops = ops = ops or DEFAULT_OPS
         self.tp_exact = tp_exact
-        import os as _os
-        self.fuse_attn_quant = _os.environ.get("QS_UNFUSED_ATTN_QUANT") is None  # A/B hook: attention + separate per-token quant kernel
+        self.fuse_attn_quant = True  # measured (profiles/r02_notes.md): attention + a separate per-token quant kernel is 1.3 % slower per step
         self.no_comm = no_comm  # debugging: run one rank's shard of a tensor-parallel model without the collectives (sanitizer / profiler runs)
         # tensor parallel, fused path: the all-reduce of the row-parallel GEMM outputs is folded into the following add+norm+quant kernel
         # (peer loads over NVLink symmetric memory) instead of an NCCL call

@@ -16,8 +16,9 @@ ap.add_argument("--exact", action="store_true")
 ap.add_argument("--layers", type=int, default=2)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--tp", type=int, default=2)
+ap.add_argument("--model", default="qwen1.5-72b")
 a = ap.parse_args()
-run = DecodeRunner("qwen1.5-72b", "w4a8kv4", 64, 1024, torch.device("cuda:0"), tp_rank=1, tp_size=a.tp, layers=a.layers, fused=True, tp_exact=a.exact, no_comm=True)
+run = DecodeRunner(a.model, "w4a8kv4", 64, 1024, torch.device("cuda:0"), tp_rank=min(1, a.tp - 1), tp_size=a.tp, layers=a.layers, fused=True, tp_exact=a.exact, no_comm=True)
 with torch.no_grad():
     for _ in range(2):
         tok = run.forward(run.tokens_in)
