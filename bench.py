@@ -535,17 +535,8 @@ def tp_block(args, rank, world, dev, hbm_gbs):
         want_peer = bool(ok.item() > 0)
     run = DecodeRunner(args.tp_model, "w4a8kv4", args.batch, args.ctx, dev, tp_rank=rank, tp_size=world, seed=rank, layers=args.tp_layers,
                        fused=True, tp_exact=args.tp_exact, tp_peer=want_peer)
-    # the exact (parity) mode adds a tiny [M] fp32 max-all-reduce per row-parallel GEMM; it is measured with eager launches (inside a captured
-    # graph that NCCL call failed on one rank of the 2-GPU box with "unspecified launch failure": not root-caused, the mode is the parity mode, not
-    # the throughput mode)
-    eager = bool(args.tp_exact and world > 1)
-    if eager:
-        for _ in range(2):
-            run.tokens_out.copy_(run.forward(run.tokens_in))
-        step_fn = lambda: run.tokens_out.copy_(run.forward(run.tokens_in))
-    else:
-        run.capture()
-        step_fn = run.step
+    run.capture()
+    step_fn = run.step
     stream = torch.cuda.current_stream()
     steps = max(5, min(args.steps, 20))
 
@@ -582,7 +573,7 @@ def tp_block(args, rank, world, dev, hbm_gbs):
     L = run.L
     sb = step_bytes(cfg, "w4a8kv4", args.batch, args.ctx, L, world)
     rec = {"model": cfg.name, "precision": "w4a8kv4", "batch": args.batch, "ctx": args.ctx, "layers": L, "tp": world, "steps": steps,
-           "quant_mode": "exact (global per-token amax, SURVEY 8e parity rule; eager launches)" if args.tp_exact else "throughput (per-rank local amax)",
+           "quant_mode": "exact (global per-token amax, SURVEY 8e parity rule)" if args.tp_exact else "throughput (per-rank local amax)",
            "tokens_per_s": args.batch / (ms * 1e-3), "ms_per_step": ms, "per_rank_hbm_bytes_per_step": sb,
            "per_rank_hbm_frac": sb / (ms * 1e-3) / 1e9 / hbm_gbs,
            "allreduce": None if world == 1 else {"calls_per_step": 2 * L, "message_bytes": args.batch * cfg.hidden * 2, "us_per_call_isolated": ar_us,

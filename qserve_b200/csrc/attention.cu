@@ -155,10 +155,16 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
   __shared__ __align__(8) uint64_t s_full[kWarps][R];
   __shared__ uint32_t s_last;
 
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kWarps * R; ++i) mbar_init(&s_full[0][0] + i, 1);
+  // Every warp initialises the barriers of ITS OWN ring (lane 0, the lane that later arms them and issues the copies), so no block-wide
+  // barrier is needed between initialisation and first use.  Round 1 let thread 0 initialise all rings without a barrier: harmless while every
+  // CTA of a single-wave launch sat in griddepcontrol.wait long enough, but a late CTA of a multi-wave launch (64 kv heads x 64 sequences =
+  // 4096 CTAs at Qwen1.5-72B) could arm a ring before thread 0 had initialised it -- the initialisation then wiped the pending transaction
+  // count and that warp waited forever (found in round 2: one hung warp per ~10^8 slices, profiles/r02_notes.md).
+  if (lane == 0) {
+    for (int i = 0; i < R; ++i) mbar_init(&s_full[warp][i], 1);
     fence_barrier_init();
   }
+  __syncwarp();
 #define ATTN_PROF(slot) do { if (prof) prof[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = attn_gtime(); } while (0)
   if (threadIdx.x == 0) ATTN_PROF(0);
   qs_trace(QS_K_ATTN, 0);

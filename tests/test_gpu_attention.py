@@ -194,3 +194,28 @@ def test_attention_argument_errors(dev):
         fa.single_query_attention(q, k, k, table, lens, None, 8192, 64, Hkv * D, 1, D, 1e4, True, True, True)
     with pytest.raises(RuntimeError):  # kv cache without zero points is never produced by the engine (arg_utils.py:422)
         fa.single_query_attention(q, k, k, table, lens, None, 8192, 64, Hkv * D // 2, 1, D, 1e4, True, True, False)
+
+
+def test_multi_wave_launches_are_stable(dev):
+    """Regression (round 2): more CTAs than resident slots (4 per SM).  A late CTA of a multi-wave launch does not sit in
+    griddepcontrol.wait, so its warps reach their first bulk copy immediately; in round 1 thread 0 initialised every warp's
+    ring barriers without a block barrier, and a warp that armed its ring first lost its transaction count and hung (one
+    warp in ~1e8 slices: seen only at Qwen1.5-72B size, 4096 CTAs per launch).  Many back-to-back launches must all finish
+    and reproduce the first result bit for bit."""
+    import qserve_backend.fused_attention as fa
+    from qserve_b200.decode import DecodeRunner
+
+    B = 192  # x 8 kv heads = 1536 CTAs, 592 resident slots
+    run = DecodeRunner("llama-3-8b", "w4a8kv4", batch=B, ctx=200, device=dev, layers=1, fused=False, seed=11)
+    g = torch.Generator(device=dev).manual_seed(3)
+    run.qkv_buf.copy_(torch.randn(run.qkv_buf.shape, device=dev, generator=g).half())
+    D = 128
+    q, k, v = run.qkv_buf.split([run.q_size, run.kv_size, run.kv_size], dim=-1)
+    q, k, v = q.reshape(B, run.Hq, D), k.reshape(B, run.Hkv, D), v.reshape(B, run.Hkv, D)
+    args = (q, k, v, run.block_tables[0], run.context_lens, None, 8192, 64, run.size_per_token, run.max_seq_len, D, run.cfg.rope_theta, True, True, True)
+    first = fa.single_query_attention(*args).clone()
+    for _ in range(400):
+        out = fa.single_query_attention(*args)
+    torch.cuda.synchronize()
+    assert torch.equal(out, first)
+    assert torch.isfinite(first.float()).all()
