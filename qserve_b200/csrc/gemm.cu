@@ -165,6 +165,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   using C = Cfg<MODE, NT, WS, AS>;
   constexpr int kActStages = AS;
   constexpr int TA = C::kTA > 0 ? C::kTA : 1;
+  // The two MMA issuers take alternate iterations, so on a ring of ODD depth each issuer sees only every other phase of a given barrier and a
+  // parity wait could be satisfied by the phase before the one it skipped.  W4A8 is safe for any depth: an issuer first waits for the TMEM A stage of
+  // its iteration, which the (in-order) unpack warps can only fill after the OTHER issuer's commit for the iteration three back -- and that issuer
+  // had waited for the very activation / weight phase in question.  W8A8 has no such guard (operands come straight from TMA-completed barriers,
+  // which may complete out of order): its rings must have even depth, so that every barrier belongs to one issuer and is observed phase by phase.
+  // (Round 2: a 3-deep W8A8 weight ring produced a launch failure in the first test that used it.)
+  static_assert(MODE != kModeW8 || (WS % 2 == 0 && AS % 2 == 0), "W8A8: ring depths must be even (two alternating MMA issuers)");
   extern __shared__ __align__(1024) uint8_t smem[];  // no static shared memory in this kernel: the window starts 1024-aligned
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* s_act = smem + C::kOffAct;
@@ -680,7 +687,13 @@ int dispatch_gemm(const GemmArgs& a) {
     nt = a.M <= 32 ? 32 : a.M <= 64 ? 64 : 128;
   }
   if (nt == 32) return launch_gemm<MODE, 32, (w8 ? 2 : grp ? 4 : 5), 4>(a);
-  if (nt == 64) return launch_gemm<MODE, 64, (w8 ? 2 : grp ? 3 : 4), 3>(a);
+  if (nt == 64) return launch_gemm<MODE, 64, (w8 ? 2 : grp ? 3 : 4), (w8 ? 2 : 3)>(a);
+  if constexpr (w8) {
+    // W8A8 at 65..128 tokens: the 4-deep weight ring (4 x 32 KB) leaves no room for the split-K receive buffer, so the narrow layers of a batch-128
+    // step ran on 32-48 CTAs (down_proj 35 us = 0.25 of the HBM peak).  Layers that want a split take a 2-deep ring (even depth: see the kernel).
+    const int tiles = (a.N / kBM) * ((a.M + 127) / 128);
+    if (a.force_split != 1 && tiles * 2 <= num_sms()) return launch_gemm<MODE, 128, 2, 2>(a);
+  }
   return launch_gemm<MODE, 128, (w8 ? 4 : 2), 2>(a);
 }
 
