@@ -678,10 +678,13 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       __threadfence();
       const int nvec = num_heads * kD / 8;
       const uint4* row = reinterpret_cast<const uint4*>(out + static_cast<size_t>(b) * num_heads * kD);
+      // one pass: the row (<= kRowRegs x 128 vectors: up to 64 query heads) stays in registers between the statistics and the quantisation
+      constexpr int kRowRegs = 8;
+      const bool in_regs = nvec <= kRowRegs * kAttnThreadsV2;
+      uint4 rv[kRowRegs];
       float amax = 0.f;
       long long sum = 0;
-      for (int i = threadIdx.x; i < nvec; i += kAttnThreadsV2) {
-        const uint4 v = __ldcg(row + i);
+      auto stats = [&](const uint4& v) {
         const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -689,6 +692,18 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
           if (q_sum) sum += __float2ll_rn(f.x * 16777216.f) + __float2ll_rn(f.y * 16777216.f);
           amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
         }
+      };
+      if (in_regs) {
+#pragma unroll
+        for (int c = 0; c < kRowRegs; ++c) {
+          const int i = threadIdx.x + c * kAttnThreadsV2;
+          rv[c] = (i < nvec) ? __ldcg(row + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int c = 0; c < kRowRegs; ++c)
+          if (threadIdx.x + c * kAttnThreadsV2 < nvec) stats(rv[c]);
+      } else {
+        for (int i = threadIdx.x; i < nvec; i += kAttnThreadsV2) stats(__ldcg(row + i));
       }
 #pragma unroll
       for (int m = 16; m >= 1; m >>= 1) {
@@ -706,8 +721,7 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
       }
       const float qs_ = __fdiv_rn(127.f, amax);
       uint2* qrow = reinterpret_cast<uint2*>(q_out + static_cast<size_t>(b) * num_heads * kD);
-      for (int i = threadIdx.x; i < nvec; i += kAttnThreadsV2) {
-        const uint4 v = __ldcg(row + i);
+      auto quantise = [&](int i, const uint4& v) {
         const __half* h = reinterpret_cast<const __half*>(&v);
         uint32_t w[2] = {0u, 0u};
 #pragma unroll
@@ -717,6 +731,15 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
           w[j >> 2] |= (static_cast<uint32_t>(c) & 0xffu) << ((j & 3) * 8);
         }
         qrow[i] = make_uint2(w[0], w[1]);
+      };
+      if (in_regs) {
+#pragma unroll
+        for (int c = 0; c < kRowRegs; ++c) {
+          const int i = threadIdx.x + c * kAttnThreadsV2;
+          if (i < nvec) quantise(i, rv[c]);
+        }
+      } else {
+        for (int i = threadIdx.x; i < nvec; i += kAttnThreadsV2) quantise(i, __ldcg(row + i));
       }
     }
   }

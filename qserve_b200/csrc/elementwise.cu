@@ -641,6 +641,69 @@ __global__ void __launch_bounds__(kThreads) quant_given_amax_kernel(int8_t* __re
   if (threadIdx.x == 0) scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
 }
 
+// Register-resident form of quant_per_token_kernel for rows of at most 4 x 512 vectors (H <= 16384: every benchmark shape): one global pass, the
+// max and the exact sum are reduced behind a single barrier.  Same arithmetic: bit-identical results.
+template <int CH>
+__global__ void __launch_bounds__(kThreads) quant_per_token_fast_kernel(int8_t* __restrict__ out, const __half* __restrict__ in,
+                                                                       __half* __restrict__ input_sum, __half* __restrict__ scale, int H) {
+  __shared__ float red[32];
+  __shared__ long long red_ll[32];
+  const int row = blockIdx.x;
+  const int nvec = H / 8;
+  qs_trace(QS_K_QUANT, 0);
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  qs_trace(QS_K_QUANT, 1);
+  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(row) * H);
+  uint4 xv[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = threadIdx.x + c * kThreads;
+    xv[c] = (i < nvec) ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float amax = 0.f;
+  long long s = 0;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (threadIdx.x + c * kThreads < nvec) {
+      const __half2* h = reinterpret_cast<const __half2*>(&xv[c]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        if (input_sum) s += fx_of_half(f.x) + fx_of_half(f.y);
+        amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+      }
+    }
+  }
+  amax = warp_reduce(amax, OpMax());
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[w] = amax; red_ll[w] = s; }
+  __syncthreads();
+  amax = (l < (kThreads >> 5)) ? red[l] : 0.f;
+  amax = warp_reduce(amax, OpMax());
+  if (input_sum && threadIdx.x < 32) {
+    long long total = (l < (kThreads >> 5)) ? red_ll[l] : 0ll;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+    if (threadIdx.x == 0) input_sum[row] = __float2half_rn(fx_to_float(total));
+  }
+  if (threadIdx.x == 0) scale[row] = __float2half_rn(__fdiv_rn(amax, 127.f));
+  const float qs_ = __fdiv_rn(127.f, amax);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = threadIdx.x + c * kThreads;
+    if (i < nvec) {
+      const __half* h = reinterpret_cast<const __half*>(&xv[c]);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = __half2float(h[j]);
+      store_q8(out + static_cast<size_t>(row) * H, i, x, qs_);
+    }
+  }
+}
+
 __global__ void quant_scalar_kernel(int8_t* __restrict__ out, const __half* __restrict__ in, float scale, size_t n) {
   if (threadIdx.x == 0) pdl_launch_dependents();
   pdl_wait();
@@ -1151,6 +1214,16 @@ int layernorm_general_quant(void* out_q, const void* in, const void* gamma, void
 int quant_per_token(void* out_q, const void* in, void* input_sum, void* scale, int tokens, int hidden, void* stream) {
   if (tokens == 0) return QS_OK;
   QS_REQUIRE(hidden > 0 && hidden % 8 == 0, "invoke_quant: hidden=%d must be a positive multiple of 8", hidden);
+  {
+    const int nvec = hidden / 8;
+    auto go = [&](auto kern) {
+      return launch(kern, dim3(tokens), dim3(kThreads), 0, stream, "invoke_quant", static_cast<int8_t*>(out_q), static_cast<const __half*>(in),
+                    static_cast<__half*>(input_sum), static_cast<__half*>(scale), hidden);
+    };
+    if (nvec <= kThreads) return go(quant_per_token_fast_kernel<1>);
+    if (nvec <= 2 * kThreads) return go(quant_per_token_fast_kernel<2>);
+    if (nvec <= 4 * kThreads) return go(quant_per_token_fast_kernel<4>);
+  }
   const size_t smem = static_cast<size_t>(hidden) * 2;
   int rc = ensure_smem(quant_per_token_kernel, smem, "invoke_quant");
   if (rc) return rc;
