@@ -44,7 +44,13 @@ typedef enum qs_status {
 
 QS_API int qs_abi_version(void);
 QS_API const char* qs_last_error(void);
-/* Enable (1) / disable (0) programmatic dependent launch for all subsequent launches; returns the previous value. */
+/* Enable (1) / disable (0) programmatic dependent launch for all subsequent launches; returns the previous value.
+ * With PDL on (default) every kernel runs `griddepcontrol.launch_dependents` at entry and reads STATIC operands -- weights, weight scales,
+ * level-2 parameters, the page-pointer table, length_per_sample -- BEFORE `griddepcontrol.wait`, so that its prologue overlaps the previous
+ * kernel.  Those tensors must therefore not be written by a kernel of the same stream inside a chain of back-to-back library calls (update block
+ * tables / context lengths from the host, as the reference's ModelRunner does, or behind a non-library kernel).  The controls of this header
+ * (qs_set_pdl, qs_gemm_force_*, ...) are process-wide and unsynchronised; qs_last_error() is thread-local.  Host-side caches (kernel
+ * attributes, SM count, tensor maps) are keyed by the CURRENT device: make the tensors' device current before calling (the Python mirror does). */
 QS_API int qs_set_pdl(int enabled);
 
 /* ---------------------------------------------------------------------------------------------------------
