@@ -115,6 +115,15 @@ QS_API int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens
                                        float rotary_embedding_base, int rotary_embedding_max_positions, int neox_rotary_style,
                                        int int4_kv_cache, int kv_cache_with_zeros, void* stream);
 
+/* Prompt-phase attention: replaces the third-party call flash_attn.flash_attn_varlen_func(q, k, v, cu_seqlens, cu_seqlens, max_seqlen,
+ *   max_seqlen, dropout_p=0.0, causal=True) at qserve/modeling/models/llama_w4a8_unpad.py:232-242.
+ *   q [T,Hq,128], k / v [T,Hkv,128] fp16: strided views of the qkv buffer apply_bias_rope_update_kv_cache has rotated in place (row strides in
+ *   halfs, multiples of 8); cu_seqlens int32 [batch+1] shared by queries and keys; out fp16 [T,Hq,128].  Causal, no dropout, GQA by
+ *   Hq / Hkv.  fp32 softmax, P rounded to fp16 before the second MMA (as flash-attn does); tcgen05 kind::f16, sm_100a only.              */
+QS_API int qs_prefill_attention(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride, int64_t v_stride, void* out,
+                         int64_t out_stride, const int32_t* cu_seqlens, int batch, int num_tokens, int max_seqlen, int num_heads,
+                         int num_kv_heads, int head_dim, float softmax_scale, void* stream);
+
 /* qserve_backend.fused_attention.compute_padding_offsets         kernels/csrc/fused_attention/input_metadata_helper.cu:33-45 */
 QS_API int qs_compute_padding_offsets(int32_t* padding_offsets, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream);
 

@@ -169,6 +169,16 @@ int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens, const
   return prefill_rope_append(a);
 }
 
+int qs_prefill_attention(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride, int64_t v_stride, void* out,
+                         int64_t out_stride, const int32_t* cu_seqlens, int batch, int num_tokens, int max_seqlen, int num_heads, int num_kv_heads,
+                         int head_dim, float softmax_scale, void* stream) {
+  PrefillAttnArgs a;
+  a.q = q; a.k = k; a.v = v; a.out = out; a.q_stride = q_stride; a.k_stride = k_stride; a.v_stride = v_stride; a.out_stride = out_stride;
+  a.cu_seqlens = cu_seqlens; a.batch = batch; a.num_tokens = num_tokens; a.max_seqlen = max_seqlen; a.num_heads = num_heads;
+  a.num_kv_heads = num_kv_heads; a.head_dim = head_dim; a.softmax_scale = softmax_scale; a.stream = stream;
+  return prefill_attention(a);
+}
+
 int qs_compute_padding_offsets(int32_t* out, const int32_t* cu_seqlens, int batch, int max_seqlen, void* stream) {
   QS_REQUIRE(out && cu_seqlens, "compute_padding_offsets: null tensor");
   return padding_offsets(out, cu_seqlens, batch, max_seqlen, stream);

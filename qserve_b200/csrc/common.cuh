@@ -198,6 +198,56 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- cta_group::2 (a pair of CTAs on the two SMs of a TPC drives ONE 256-row UMMA; only the even CTA issues) ----
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result) {  // executed by one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem, 256 rows over both CTAs] (+)= A[tmem of each CTA, its 128 rows] * B[shared memory, each CTA holds half of the N columns]
+__device__ __forceinline__ void umma_i8_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrive (once all previously issued MMAs of this thread have completed) on the mbarrier at this CTA-relative offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+// 2-D tiled load into THIS CTA's shared memory whose completion is signalled on the mbarrier at the same CTA-relative offset in CTA 0 of the pair
+// (cta_group::2 form: the barrier may live in either CTA of the pair, so one barrier of the MMA-issuing CTA collects both halves of a stage)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, int32_t x, int32_t y, uint64_t* bar) {
+  uint32_t leader_bar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(leader_bar) : "r"(smem_u32(bar)), "r"(0u));
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(leader_bar), "r"(x), "r"(y)
+      : "memory");
+}
+// named barrier over `threads` threads (a multiple of 32) of the CTA; id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// arrive on the mbarrier at the same CTA-relative offset in CTA `rank` of the cluster.  Default semantics (release at CTA scope) on purpose:
+// `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive (and `try_wait.acquire.cluster` to a CCTL.IVALL behind the wait),
+// ~1 us per pipeline stage.  The data these barriers guard is tensor memory / TMA-written shared memory, ordered by tcgen05.wait::st +
+// tcgen05.fence::before_thread_sync on the producer side and tcgen05.fence::after_thread_sync on the consumer side, not by generic-proxy fences;
+// the consumer waits with the ordinary mbar_wait.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 // 16 lanes x 128 bit (4 columns) pattern, repeated twice along columns: thread t writes
 //   r0 -> (lane t/4,   col t%4)   r1 -> (lane t/4+8, col t%4)   r2 -> (lane t/4, col 4+t%4)   r3 -> (lane t/4+8, col 4+t%4)
 __device__ __forceinline__ void tmem_st_16x128b_x2(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {

@@ -29,6 +29,7 @@
 //     IEEE fp32 in the reference's source order (bit-exact against the oracle).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -44,6 +45,7 @@ constexpr int kBM = 128;  // output channels per tile (UMMA M)
 constexpr int kBK = 128;  // K sub-block (= one g128 group, one 128-byte swizzled activation row)
 constexpr int kSub = 2;    // sub-blocks per pipeline stage: per-stage barrier latencies are amortised over 256 K
 constexpr int kNumThreads = 256;
+constexpr int kPairThreads = 384;  // gemm_pair_kernel: the 8 warps of gemm_kernel + 4 more epilogue warps
 // warp roles: 0 weight producer | 1 TMEM owner + MMA issuer (even stages) | 2..5 unpack + TMEM epilogue | 6 activation producer |
 // 7 MMA issuer (odd stages).
 // All eight warps take part in the final reduce / scale / store phase.
@@ -516,6 +518,341 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
+// =============================================================================================
+// Prefill tiles (M >= 512, W4A8): a PAIR of CTAs on the two SMs of a TPC computes 256-channel x 256-token tiles with cta_group::2 UMMAs,
+// persistently (one pair per TPC walks the tile list).
+//
+// Why: with 128-token tiles every CTA pulls its whole 128 x K weight band AND its whole 128 x K activation band out of L2: M = 4096 x N = 28672 x
+// K = 4096 moves 5.5 GB L2 -> SM in 413 us = 13 TB/s, which IS the chip's L2 throughput (~6300 B/clk, B300_MICROARCH.md) -- the tensor pipe idles
+// at 52 %.  In a CTA pair each SM unpacks its own 128 channels into its own tensor memory (A operand) but stages only HALF of the 256 tokens of
+// the activation tile (B operand); the 2-CTA MMA reads the other half from the peer SM.  L2 -> SM traffic halves (2.7 GB for the shape above).
+// The first version of this kernel (one tile per launch-time CTA pair, 1 pair per TPC because of its 512 TMEM columns) lost all of that again to
+// un-overlapped per-tile fill / drain (24 us per tile for 8.3 us of MMA work; profiles/r02_notes.md), hence the persistent form: operand rings run
+// across tile boundaries, the only exposed per-tile cost is the accumulator drain (TMEM -> registers -> global, no shared-memory staging).
+//
+// Roles per CTA (384 threads): warp 0 weight producer | warp 1 TMEM allocator, leader: MMA issuer (even stages) | warps 2..5 unpack + epilogue |
+// warp 6 activation producer (both CTAs signal the LEADER's "full" barrier: cta_group::2 TMA) | warp 7 leader: MMA issuer (odd stages) |
+// warps 8..11 epilogue only (a lone warp per scheduler issues one instruction per clock: four warps needed 9 us to drain a tile, eight 2 x fewer).
+// Only the even CTA of the pair (the leader) issues MMAs; its commits are multicast to the "empty" barriers of both CTAs.  All rings have even
+// depth (two alternating issuers, see gemm_kernel).  The accumulator is zero-filled by the epilogue warps (tcgen05.st) and every MMA accumulates:
+// the two issuers' first instructions of a tile are not ordered against each other.
+// =============================================================================================
+template <int MODE>
+struct PairCfg {
+  static constexpr int NT = 256;                       // tokens per pair tile (UMMA N)
+  static constexpr int NH = NT / 2;                    // tokens staged per CTA
+  static constexpr int WS = 4, AS = 4, TA = 4;         // powers of two (stage = iteration & (depth - 1))
+  static constexpr int kActSub = NH * kBK;             // 16 KB: one swizzled [128 x 128 B] activation sub-tile (this CTA's half)
+  static constexpr int kActBytes = kSub * kActSub;     // 32 KB per stage
+  static constexpr int kWSub = kBM * kBK / 2;          // 8 KB packed INT4 per 128-K sub-block
+  static constexpr int kWBytes = kSub * kWSub;         // 16 KB per stage
+  static constexpr int kS2Sub = (MODE == kModeW4Grp) ? 2 * kBM : 0;
+  static constexpr int kS2Bytes = kSub * kS2Sub;
+  static constexpr int kWStageTx = kWBytes + kS2Bytes;
+  static constexpr int kAStageCols = kSub * (kBK / 4);  // 64 TMEM columns per unpacked-A stage
+  static constexpr int kTmemCols = 512;                 // 256 accumulator columns + 4 x 64 A-ring columns
+  static constexpr int kOffAct = 0;
+  static constexpr int kOffW = AS * kActBytes;          // 128 KB
+  static constexpr int kOffS2 = kOffW + WS * kWBytes;
+  static constexpr int kPipeBytes = kOffS2 + WS * kS2Bytes;
+  static constexpr int kOffRow = kPipeBytes;            // float ascales[2][NT], asums[2][NT] (double-buffered by tile parity)
+  static constexpr int kOffBar = kOffRow + 4 * NT * 4;
+  static constexpr int kNumBars = 2 * WS + 2 * AS + 2 * TA + 2;
+  static constexpr int kOffMisc = kOffBar + kNumBars * 8;
+  static constexpr int kSmemBytes = kOffMisc + 16;
+  static_assert(kSmemBytes <= 226 * 1024, "shared memory overflow");
+};
+
+template <int MODE, bool ACC>
+__global__ void __launch_bounds__(kPairThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+  using C = PairCfg<MODE>;
+  constexpr int NT = C::NT, WS = C::WS, AS = C::AS, TA = C::TA;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* s_act = smem + C::kOffAct;
+  uint8_t* s_w = smem + C::kOffW;
+  uint8_t* s_s2 = smem + C::kOffS2;
+  float* s_row = reinterpret_cast<float*>(smem + C::kOffRow);
+  uint64_t* bar_wfull = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* bar_wempty = bar_wfull + WS;
+  uint64_t* bar_xfull = bar_wempty + WS;    // leader only: BOTH halves of the activation stage have landed (the peer's TMA signals it remotely)
+  uint64_t* bar_xempty = bar_xfull + AS;    // MMA commit (multicast) -> this CTA's activation producer
+  uint64_t* bar_afull = bar_xempty + AS;    // leader only: 8 arrivals = the four unpack warps of both CTAs
+  uint64_t* bar_aempty = bar_afull + TA;    // MMA commit (multicast) -> this CTA's unpack warps
+  uint64_t* bar_dfull = bar_aempty + TA;    // both MMA issuers' last commits of a tile (multicast): accumulators complete
+  uint64_t* bar_zero = bar_dfull + 1;       // leader only: accumulators of both CTAs drained and zero-filled (16 arrivals: 8 epilogue warps each)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + C::kOffMisc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int n_pairs = static_cast<int>(gridDim.x) >> 1;
+  const int pair = static_cast<int>(blockIdx.x) >> 1;
+  const int total = p.m_tiles * ((p.N / kBM) >> 1);
+  const int my_tiles = (total - pair + n_pairs - 1) / n_pairs;  // >= 1: the host launches at most `total` pairs
+  const int n_kb = p.kb_per_tile;
+  qs_trace(QS_K_GEMM, 0);
+  if (threadIdx.x == 0) QS_PROF(0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_act);
+    tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < WS; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 4); }
+    for (int i = 0; i < AS; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
+    for (int i = 0; i < TA; ++i) { mbar_init(&bar_afull[i], 8); mbar_init(&bar_aempty[i], 1); }
+    mbar_init(bar_dfull, 2);
+    mbar_init(bar_zero, 16);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<C::kTmemCols>(s_tmem);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before anything arrives on them remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  if (threadIdx.x == 0) { pdl_launch_dependents(); QS_PROF(1); }
+
+  // tile t of this pair: the m index runs fastest, so the pairs working at the same time share a few weight bands and the whole activation matrix in L2
+  auto tile_m = [&](int lt) { return (pair + lt * n_pairs) % p.m_tiles; };
+  auto tile_n = [&](int lt) { return 2 * ((pair + lt * n_pairs) / p.m_tiles) + static_cast<int>(rank); };
+
+  if (warp == 0) {
+    // ===================================== weight producer (static data: never waits for the previous kernel) =====================================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int n_tile = tile_n(lt);
+        const int w_row = n_tile * 4;
+        const uint8_t* s2s = p.s2_scales + static_cast<size_t>(n_tile) * kBM;
+        const uint8_t* s2z = p.s2_zeros + static_cast<size_t>(n_tile) * kBM;
+        for (int it = 0; it < n_kb; ++it) {
+          mbar_wait(&bar_wempty[s], ph ^ 1);  // a fresh barrier passes the wait on the "previous" phase
+          mbar_expect_tx(&bar_wfull[s], C::kWStageTx);
+#pragma unroll
+          for (int u = 0; u < kSub; ++u) {
+            const int kb = it * kSub + u;
+            tma_load_2d(s_w + s * C::kWBytes + u * C::kWSub, &tmap_w, kb * 256, w_row, &bar_wfull[s]);
+            if constexpr (MODE == kModeW4Grp) {
+              const int kg = kb < p.K / kBK ? kb : p.K / kBK - 1;
+              bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub, s2s + static_cast<size_t>(kg) * p.N, kBM, &bar_wfull[s]);
+              bulk_copy_g2s(s_s2 + s * C::kS2Bytes + u * C::kS2Sub + kBM, s2z + static_cast<size_t>(kg) * p.N, kBM, &bar_wfull[s]);
+            }
+          }
+          if (++s == WS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================================== activation producer: this CTA's 128 of the tile's 256 tokens =====================================
+    if (lane == 0) {
+      pdl_wait();
+      qs_trace(QS_K_GEMM, 1, 6 * 32);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int a_row = tile_m(lt) * NT + static_cast<int>(rank) * C::NH;
+        for (int it = 0; it < n_kb; ++it) {
+          mbar_wait(&bar_xempty[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&bar_xfull[s], 2 * C::kActBytes);  // my half + the peer's half
+#pragma unroll
+          for (int u = 0; u < kSub; ++u)
+            tma_load_2d_pair(s_act + s * C::kActBytes + u * C::kActSub, &tmap_act, (it * kSub + u) * kBK, a_row, &bar_xfull[s]);
+          if (++s == AS) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (leader && (warp == 1 || warp == 7)) {
+    // ===================================== leader: two MMA issuers (even / odd iterations), 256 x 256 x 32 INT8 UMMAs over both SMs ==========
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_i8(2 * kBM, NT, 1u, 1u);
+      const int g_end = my_tiles * n_kb;
+      int it = (warp == 1) ? 0 : 1;  // iteration inside the current tile
+      int lt = 0;
+      bool fresh = true;
+      for (int g = it; g < g_end; g += 2) {
+        if (fresh) {
+          mbar_wait(bar_zero, lt & 1);  // accumulators of both CTAs drained (previous tile) and zero-filled
+          fresh = false;
+          if (g == 0) QS_PROF(2);
+          if (g == n_kb) QS_PROF(6);
+        }
+        const int sa = g & (TA - 1), sx = g & (AS - 1);
+        mbar_wait(&bar_afull[sa], (g / TA) & 1);  // both CTAs' unpack warps have written their A stage
+        if (g == 0) QS_PROF(3);
+        mbar_wait(&bar_xfull[sx], (g / AS) & 1);          // both activation halves
+        if (g == 0) QS_PROF(4);
+        if (g == 8) QS_PROF(5);
+        if (g == 14) QS_PROF(13);
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < kSub; ++u) {
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(s_act + sx * C::kActBytes + u * C::kActSub));
+#pragma unroll
+          for (int t = 0; t < kBK / 32; ++t)
+            umma_i8_ts_2cta(tmem_base, tmem_base + NT + sa * C::kAStageCols + u * (kBK / 4) + t * 8, bdesc + t * 2, idesc, 1u);
+        }
+        umma_commit_2cta(&bar_aempty[sa]);
+        umma_commit_2cta(&bar_xempty[sx]);
+        it += 2;
+        if (it >= n_kb) {  // that was this issuer's last iteration of the tile (n_kb >= 2: both issuers own at least one)
+          umma_commit_2cta(bar_dfull);
+          if (lt == 0 && warp == 1) QS_PROF(7);
+          it -= n_kb;
+          ++lt;
+          fresh = true;
+        }
+      }
+    }
+  } else if ((warp >= 2 && warp <= 5) || warp >= 8) {
+    // ===================================== unpack (warps 2..5) + epilogue (warps 2..5 and 8..11), both CTAs =====================================
+    // A warp reaches the TMEM lanes 32 * (warp % 4) ..: warps w and w + 4 (mod 4 equal) share a lane quadrant and split the 256 token columns.
+    const bool unpacker = warp < 8;
+    const int quad = warp & 3;
+    const int col0 = unpacker ? 0 : NT / 2;   // first accumulator column (token) of this warp's half
+    const int epi_tid = quad * 32 + lane;     // channel inside the tile
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    auto zero_fill = [&]() {
+#pragma unroll
+      for (int c = 0; c < NT / 2; c += 8) {
+        tmem_st_16x128b_x2(trow + col0 + c, 0u, 0u, 0u, 0u);
+        tmem_st_16x128b_x2(trow + col0 + c + (16u << 16), 0u, 0u, 0u, 0u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_zero, 0);
+    };
+    zero_fill();
+    int s = 0, ta = 0;
+    uint32_t ph = 0, pha = 0;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int m_tile = tile_m(lt), n_tile = tile_n(lt);
+      if (unpacker) {
+        for (int it = 0; it < n_kb; ++it) {
+          mbar_wait(&bar_wfull[s], ph);
+          mbar_wait(&bar_aempty[ta], pha ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int u = 0; u < kSub; ++u) {
+            const uint8_t* wsrc = s_w + s * C::kWBytes + u * C::kWSub + quad * 2048 + lane * 16;
+            const uint32_t tdst = trow + NT + ta * C::kAStageCols + u * (kBK / 4);
+            uint32_t sc4 = 0, zp4 = 0;
+            if constexpr (MODE == kModeW4Grp) {
+              const uint8_t* s2 = s_s2 + s * C::kS2Bytes + u * C::kS2Sub + quad * 32 + (lane >> 2) * 4;
+              sc4 = *reinterpret_cast<const uint32_t*>(s2);
+              zp4 = *reinterpret_cast<const uint32_t*>(s2 + kBM);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint4 v = *reinterpret_cast<const uint4*>(wsrc + t * 512);
+              uint32_t xl = v.x & 0x0F0F0F0Fu, xh = (v.x >> 4) & 0x0F0F0F0Fu;
+              uint32_t yl = v.y & 0x0F0F0F0Fu, yh = (v.y >> 4) & 0x0F0F0F0Fu;
+              uint32_t zl = v.z & 0x0F0F0F0Fu, zh = (v.z >> 4) & 0x0F0F0F0Fu;
+              uint32_t wl = v.w & 0x0F0F0F0Fu, wh = (v.w >> 4) & 0x0F0F0F0Fu;
+              if constexpr (MODE == kModeW4Grp) {
+                const uint32_t s0 = sc4 & 0xFF, s1 = (sc4 >> 8) & 0xFF, s2 = (sc4 >> 16) & 0xFF, s3 = sc4 >> 24;
+                const uint32_t z0 = __byte_perm(zp4, 0, 0x0000), z1 = __byte_perm(zp4, 0, 0x1111);
+                const uint32_t z2 = __byte_perm(zp4, 0, 0x2222), z3 = __byte_perm(zp4, 0, 0x3333);
+                xl = __vadd4(xl * s0, z0); zl = __vadd4(zl * s0, z0);
+                yl = __vadd4(yl * s1, z1); wl = __vadd4(wl * s1, z1);
+                xh = __vadd4(xh * s2, z2); zh = __vadd4(zh * s2, z2);
+                yh = __vadd4(yh * s3, z3); wh = __vadd4(wh * s3, z3);
+              }
+              tmem_st_16x128b_x2(tdst + t * 8, xl, yl, zl, wl);
+              tmem_st_16x128b_x2(tdst + t * 8 + (16u << 16), xh, yh, zh, wh);
+            }
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(&bar_afull[ta], 0);  // the leader's barrier counts the unpack warps of both CTAs
+            mbar_arrive(&bar_wempty[s]);
+          }
+          if (++s == WS) { s = 0; ph ^= 1; }
+          if (++ta == TA) { ta = 0; pha ^= 1; }
+          if (epi_tid == 0 && lt == 0 && it == 8) QS_PROF(14);
+        }
+        if (epi_tid == 0 && lt == 0) QS_PROF(8);
+      }
+      // ------------------------------ epilogue: this CTA's 128 channels x 256 tokens, TMEM -> registers -> global ------------------------------
+      // thread = one channel (TMEM lane) x 128 tokens; a warp's store covers 32 consecutive channels of one token = 64 B (two full sectors)
+      pdl_wait();
+      const int m0 = m_tile * NT;
+      float* s_asc = s_row + (lt & 1) * 2 * NT;  // double-buffered by tile parity: a fast warp may already fill the next tile's values
+      float* s_asum = s_asc + NT;
+      {
+        const int j = col0 + epi_tid;  // the eight epilogue warps fetch one token's scales each
+        const bool ok = (m0 + j) < p.M;
+        s_asc[j] = ok ? __half2float(p.ascales[m0 + j]) : 0.f;
+        if constexpr (MODE == kModeW4Chn) s_asum[j] = ok ? __half2float(p.a_ssums[m0 + j]) : 0.f;
+      }
+      const int n = n_tile * kBM + epi_tid;
+      const float ws = __half2float(__ldg(p.wscales + n));
+      float wz = 0.f;
+      if constexpr (MODE == kModeW4Chn) wz = __half2float(__ldg(p.w_szs + n));
+      named_bar_sync(1, 256);  // the eight epilogue warps: per-token scales visible
+      mbar_wait(bar_dfull, lt & 1);  // every MMA of the tile has retired
+      if (epi_tid == 0 && lt == 0 && unpacker) QS_PROF(9);
+      tc_fence_after();
+      const int tok_end = min(NT, p.M - m0);
+#pragma unroll 1
+      for (int c = 0; c < NT / 64; ++c) {
+        const int tok0 = col0 + c * 32;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(trow + tok0, r);
+        tmem_wait_ld();
+        __half* out = p.out + static_cast<size_t>(m0 + tok0) * p.N + n;
+        if (tok0 + 32 <= tok_end) {
+          // whole chunk inside M: no per-token branches, the scales come in as vectors, 32 independent chains
+          float as[32], am[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(s_asc + tok0 + i);
+            as[i] = a4.x; as[i + 1] = a4.y; as[i + 2] = a4.z; as[i + 3] = a4.w;
+            if constexpr (MODE == kModeW4Chn) {
+              const float4 m4 = *reinterpret_cast<const float4*>(s_asum + tok0 + i);
+              am[i] = m4.x; am[i + 1] = m4.y; am[i + 2] = m4.z; am[i + 3] = m4.w;
+            } else {
+              am[i] = am[i + 1] = am[i + 2] = am[i + 3] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float o = epilogue_one<MODE>(static_cast<int32_t>(r[i]), ws, wz, as[i], am[i]);
+            out[static_cast<size_t>(i) * p.N] = __float2half_rn(o);
+            if constexpr (ACC) p.acc_out[static_cast<size_t>(m0 + tok0 + i) * p.N + n] = static_cast<int32_t>(r[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {  // (fully unrolled: a dynamic index would push r[] into local memory for the fast path as well)
+            if (tok0 + i < tok_end) {
+              const float o = epilogue_one<MODE>(static_cast<int32_t>(r[i]), ws, wz, s_asc[tok0 + i], s_asum[tok0 + i]);
+              out[static_cast<size_t>(i) * p.N] = __float2half_rn(o);
+              if constexpr (ACC) p.acc_out[static_cast<size_t>(m0 + tok0 + i) * p.N + n] = static_cast<int32_t>(r[i]);
+            }
+          }
+        }
+      }
+      if (epi_tid == 0 && lt == 0 && unpacker) QS_PROF(10);
+      if (lt + 1 < my_tiles) zero_fill();  // hands the accumulator back to the MMA issuers
+      if (epi_tid == 0 && lt == 0 && unpacker) QS_PROF(11);
+    }
+  } else {
+    pdl_wait();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still read this CTA's activation half / arrive on its barriers until its own last MMA has retired
+  qs_trace(QS_K_GEMM, 2);
+  if (threadIdx.x == 0) QS_PROF(12);
+  if (warp == 1) tmem_dealloc_2cta<C::kTmemCols>(tmem_base);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -670,6 +1007,57 @@ int launch_gemm(const GemmArgs& a) {
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, tm_act, tm_w, p), "gemm launch");
 }
 
+// prefill: CTA pairs (cta_group::2), 256 channels x 256 tokens per pair
+template <int MODE>
+int launch_gemm_pair(const GemmArgs& a) {
+  using C = PairCfg<MODE>;
+  GemmParams p{};
+  p.s2_scales = static_cast<const uint8_t*>(a.s2_scales);
+  p.s2_zeros = static_cast<const uint8_t*>(a.s2_zeros);
+  p.wscales = static_cast<const __half*>(a.wscales);
+  p.w_szs = static_cast<const __half*>(a.w_szs);
+  p.ascales = static_cast<const __half*>(a.ascales);
+  p.a_ssums = static_cast<const __half*>(a.a_ssums);
+  p.out = static_cast<__half*>(a.out);
+  p.acc_out = static_cast<int32_t*>(a.acc_out);
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  const int n_tiles = a.N / kBM;
+  p.m_tiles = (a.M + C::NT - 1) / C::NT;
+  p.kb_per_tile = (a.K + kSub * kBK - 1) / (kSub * kBK);
+  p.split = 1;
+  p.prof = static_cast<unsigned long long*>(a.prof);
+  CUtensorMap tm_act, tm_w;
+  int rc = make_tmap_u8(&tm_act, a.act, a.M, a.K, C::NH);
+  if (rc) return rc;
+  rc = make_tmap_w4(&tm_w, a.weight, a.N, a.K);
+  if (rc) return rc;
+  auto kern = a.acc_out ? gemm_pair_kernel<MODE, true> : gemm_pair_kernel<MODE, false>;
+  static bool attr_set[2][kMaxDevices] = {};
+  bool& done = attr_set[a.acc_out ? 1 : 0][device_ordinal()];
+  if (!done) {
+    rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes), "cudaFuncSetAttribute(gemm pair smem)");
+    if (rc) return rc;
+    done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  // persistent: one CTA pair per TPC walks the (m fastest) tile list with stride = number of pairs
+  const int total_pairs = (n_tiles / 2) * p.m_tiles;
+  cfg.gridDim = dim3(2 * std::min(total_pairs, num_sms() / 2));
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = static_cast<cudaStream_t>(a.stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, tm_act, tm_w, p), "gemm (pair) launch");
+}
+
 template <int MODE>
 int dispatch_gemm(const GemmArgs& a) {
   QS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem M=%d N=%d K=%d", a.M, a.N, a.K);
@@ -680,6 +1068,10 @@ int dispatch_gemm(const GemmArgs& a) {
   // weight-ring depths (256-K stages) chosen so that NT <= 128 fits two CTAs per SM (<= 113 KB smem, <= 256 TMEM columns)
   constexpr bool w8 = (MODE == kModeW8), grp = (MODE == kModeW4Grp);
   QS_REQUIRE(a.force_nt == 0 || a.force_nt == 32 || a.force_nt == 64 || a.force_nt == 128, "gemm: tile tokens must be 32, 64 or 128");
+  if constexpr (MODE != kModeW8) {
+    static const bool no_pair = getenv("QS_GEMM_NO_PAIR") != nullptr;  // A/B hook
+    if (!no_pair && a.force_nt == 0 && a.force_split == 0 && a.M >= 512 && (a.N / kBM) % 2 == 0 && a.K >= 512) return launch_gemm_pair<MODE>(a);
+  }
   int nt = a.force_nt > 0 ? a.force_nt : 0;
   if (nt == 0) {
     // prefill-sized M: 128-token tiles with TWO co-resident CTAs per SM beat the 256-token tile (one CTA per SM) by 14-15 % (M = 1024: 2071 vs

@@ -102,4 +102,18 @@ struct PrefillAppendArgs {
 int prefill_rope_append(const PrefillAppendArgs& a);
 int padding_offsets(int* out, const int* cu_seqlens, int batch, int max_seqlen, void* stream);
 
+// prefill_attention.cu: causal variable-length self-attention over the post-RoPE fp16 q / k / v of a prompt batch
+struct PrefillAttnArgs {
+  const void* q = nullptr;    // fp16 [T, Hq, 128], rows of q_stride halfs
+  const void* k = nullptr;    // fp16 [T, Hkv, 128]
+  const void* v = nullptr;
+  void* out = nullptr;        // fp16 [T, Hq, 128], rows of out_stride halfs
+  long long q_stride = 0, k_stride = 0, v_stride = 0, out_stride = 0;
+  const int* cu_seqlens = nullptr;  // [batch + 1] token offsets (q and k share them: self-attention over the prompt)
+  int batch = 0, num_tokens = 0, max_seqlen = 0, num_heads = 0, num_kv_heads = 0, head_dim = 0;
+  float softmax_scale = 0.f;
+  void* stream = nullptr;
+};
+int prefill_attention(const PrefillAttnArgs& a);
+
 }  // namespace qs
