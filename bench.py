@@ -345,6 +345,34 @@ def kernel_table(run, reps, hbm_gbs, prefill: bool = True, fused_ops: bool = Tru
                                        "frac_of_nominal_int8_dense": opsn / t / 1e12 / 4500.0, "frac_of_measured_umma_i8_peak": opsn / t / 1e12 / 4760.0,
                                        "bound": "tensor (INT8 dense: nominal 4.5 POP/s; measured tcgen05 kind::i8 issue peak 4.76 POP/s, tools/ubench/umma.cu)"}
         del big
+        if fused_ops:  # (this repo's table only: the reference-gpu arm reuses kernel_table for the reference extensions)
+            # prompt-phase attention: BASELINE config 3's prompt batch, 8 x ctx tokens, causal; flash-attn (the third-party
+            # kernel the reference calls, a library) is timed beside it when the image has it
+            from qserve_b200 import backend as _be
+            cfg = run.cfg
+            n_p, plen = 8, run.ctx
+            qkv = torch.randn(n_p * plen, (cfg.heads + 2 * cfg.kv_heads) * 128, device=run.dev).half()
+            q, k, v = qkv.split([cfg.heads * 128, cfg.kv_heads * 128, cfg.kv_heads * 128], dim=-1)
+            q, k, v = q.reshape(-1, cfg.heads, 128), k.reshape(-1, cfg.kv_heads, 128), v.reshape(-1, cfg.kv_heads, 128)
+            cu = torch.arange(0, (n_p + 1) * plen, plen, dtype=torch.int32, device=run.dev)
+            flops = n_p * 4.0 * 128 * cfg.heads * plen * (plen + 1) / 2
+            impls = {"qserve_b200": _be.flash_attn_varlen_func}
+            try:
+                from flash_attn import flash_attn_varlen_func as _fa
+                impls["flash_attn"] = _fa
+            except Exception:  # noqa: BLE001
+                pass
+            rec = {"prompts": n_p, "prompt_len": plen, "heads": cfg.heads, "kv_heads": cfg.kv_heads, "causal_flops": flops,
+                   "bound": "tensor (fp16 dense: nominal 2.25 PFLOP/s)"}
+            for name, fn in impls.items():
+                def pa(fn=fn):
+                    fn(q, k, v, cu, cu, plen, plen, dropout_p=0.0, causal=True)
+                    return 1
+                t = time_kernel(pa, max(2, reps // 2), stream, graph)
+                rec[f"us_{name}" if name != "qserve_b200" else "us"] = t * 1e6
+                rec[f"TFLOPS_{name}" if name != "qserve_b200" else "TFLOPS"] = flops / t / 1e12
+            rec["frac_of_nominal_fp16_dense"] = rec["TFLOPS"] / 2250.0
+            out["prefill_attention"] = rec
     return out
 
 
@@ -492,11 +520,18 @@ def refmodel_block(run, args, steps: int):
         lens = [plen] * n_prompts
         toks = torch.randint(0, r3.cfg.vocab, (n_prompts * plen,), device=r3.dev)
         meta = ref3.prefill_metadata(lens)
-        for _ in range(2):
-            ref3.prefill_logits(toks, lens, meta)
-        ms, host_ms = timed(lambda: ref3.prefill_logits(toks, lens, meta), 3)
+        per_impl = {}
+        for impl in ("flash_attn", "qserve_b200"):  # the prompt attention behind the reference layer's flash_attn_varlen_func call
+            ref3.use_prefill_attention(impl)
+            for _ in range(2):
+                ref3.prefill_logits(toks, lens, meta)
+            per_impl[impl] = timed(lambda: ref3.prefill_logits(toks, lens, meta), 3)
+        ms, host_ms = per_impl["qserve_b200"]
         out["config3_prefill"] = {"prompts": n_prompts, "prompt_len": plen, "tokens": n_prompts * plen, "ms_per_step": ms, "host_ms_per_step": host_ms,
-                                  "tokens_per_s": n_prompts * plen / (ms * 1e-3), "int8_TOPS_gemm_only": 2.0 * n_prompts * plen * weight_bytes(r3.cfg, "w4a8", 1) * 2 * r3.L / (ms * 1e-3) / 1e12}
+                                  "tokens_per_s": n_prompts * plen / (ms * 1e-3), "int8_TOPS_gemm_only": 2.0 * n_prompts * plen * weight_bytes(r3.cfg, "w4a8", 1) * 2 * r3.L / (ms * 1e-3) / 1e12,
+                                  "prompt_attention": "qserve_b200 tcgen05 kernel (qs_prefill_attention)",
+                                  "ms_per_step_with_flash_attn": per_impl["flash_attn"][0],
+                                  "tokens_per_s_with_flash_attn": n_prompts * plen / (per_impl["flash_attn"][0] * 1e-3)}
         decode_numbers(ref3, r3, "config3_decode")
         pf, dg = out["config3_prefill"], out["config3_decode_graph"]
         # in-flight batching round: one prompt step admits 8 sequences, then the batch decodes until they finish 512 tokens (qserve_benchmark protocol 1024 in / 512 out)

@@ -64,6 +64,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
+// 2^x on the SFU (MUFU.EX2), flush-to-zero: the argument is <= 8 here and -inf must give 0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // MN-major shared-memory operand under the 128-byte swizzle: rows of 128 B are 64 contiguous elements of the M/N dimension, one row per K
 // index.  In 16-byte units the canonical layout is ((8, n), (8, k)) : ((1, LBO), (8, SBO)): LBO = distance between 64-element column groups
 // (here the second 16 KB sub-tile), SBO = distance between groups of 8 K-rows (1024 B).
@@ -217,19 +224,25 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const bool diag = (j == qb);
       mbar_wait(bar_s, ph);
       tc_fence_after();
-      // ---- pass 1: row maximum ----
-      float m_blk = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c = 0; c < kBKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_s + c * 32, r);
-        tmem_wait_ld();
+      // ---- the whole S row (128 fp32) comes into registers with ONE TMEM round trip ----
+      uint32_t r[kBKV / 32][32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]);
-          const bool ok = !diag || (j * kBKV + c * 32 + i) <= q_pos;
-          m_blk = fmaxf(m_blk, ok ? s : -CUDART_INF_F);
-        }
+      for (int c = 0; c < kBKV / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, r[c]);
+      tmem_wait_ld();
+      float m_blk = -CUDART_INF_F;
+      if (diag) {
+#pragma unroll
+        for (int c = 0; c < kBKV / 32; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (j * kBKV + c * 32 + i > q_pos) r[c][i] = 0xff800000u;  // -inf: exp2 turns it into an exact 0
+            m_blk = fmaxf(m_blk, __uint_as_float(r[c][i]));
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < kBKV / 32; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[c][i]));
       }
       m_blk *= p.scale_log2;
       // ---- lazy rescale of O and l (warp-uniform decision) ----
@@ -240,41 +253,36 @@ prefill_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       }
       if (__any_sync(0xffffffffu, grow)) {
         const float m_new = grow ? m_blk : m_used;
-        const float alpha = (m_used == -CUDART_INF_F) ? 0.f : exp2f(m_used - m_new);  // 1 for rows that keep their maximum
+        const float alpha = (m_used == -CUDART_INF_F) ? 0.f : ex2_approx(m_used - m_new);  // 1 for rows that keep their maximum
         if (j > 0) {
 #pragma unroll 1
           for (int c = 0; c < kD / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_o + c * 32, r);
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_o + c * 32, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + c * 32, r);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + c * 32, o);
           }
         }
         l *= alpha;
         m_used = m_new;
       }
-      // ---- pass 2: P = exp2(s * scale - m_used), fp16, written over the S columns already consumed ----
-#pragma unroll 1
-      for (int c = 0; c < kBKV / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_s + c * 32, r);
-        tmem_wait_ld();
-        uint32_t pk[16];
+      // ---- P = exp2(s * scale - m_used), rounded to fp16, written over the S columns (all of S is in registers by now) ----
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const bool ok0 = !diag || (j * kBKV + c * 32 + i) <= q_pos;
-          const bool ok1 = !diag || (j * kBKV + c * 32 + i + 1) <= q_pos;
-          const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_used)) : 0.f;
-          const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_used)) : 0.f;
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[hc * 2 + (i >> 5)][i & 31]), p.scale_log2, -m_used));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[hc * 2 + (i >> 5)][(i & 31) + 1]), p.scale_log2, -m_used));
           const __half2 h2 = __floats2half2_rn(p0, p1);
           // the row sum is taken over the ROUNDED probabilities: numerator (the MMA sees fp16 P) and denominator then agree
           const float2 f = __half22float2(h2);
           l += f.x + f.y;
           pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        tmem_st_32x32b_x16(t_s + c * 16, pk);  // columns [16c, 16c + 16) lie inside S chunk c / 2, which this thread has already read
+        tmem_st_32x32b_x32(t_s + hc * 32, pk);
       }
       tmem_wait_st();
       tc_fence_before();

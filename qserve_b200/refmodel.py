@@ -51,6 +51,14 @@ def import_reference(w8a8: bool = False):
         sys.modules["xformers"], sys.modules["xformers.ops"] = xf, xo
     import qserve_backend  # noqa: F401
     assert os.path.dirname(os.path.abspath(qserve_backend.__file__)).startswith(_ROOT), "qserve_backend does not resolve to this repo"
+    try:
+        import flash_attn  # noqa: F401  (third-party prompt attention, imported at module scope by llama_w4a8_unpad.py:27)
+    except Exception:  # noqa: BLE001  not installed: the reference then runs on this repo's prompt attention alone
+        from qserve_b200 import backend
+        fa = types.ModuleType("flash_attn")
+        fa.flash_attn_varlen_func = backend.flash_attn_varlen_func
+        fa.__version__ = "qserve_b200"
+        sys.modules["flash_attn"] = fa
     name = "qserve.modeling.models.llama_w8a8_unpad" if w8a8 else "qserve.modeling.models.llama_w4a8_unpad"
     return importlib.import_module(name)
 
@@ -83,6 +91,16 @@ class RefModel:
         self.model = model
         self._share_weights()
         self._meta = None
+        self._flash_attn = mod.flash_attn_varlen_func  # whatever `from flash_attn import flash_attn_varlen_func` bound (llama_w4a8_unpad.py:27)
+
+    def use_prefill_attention(self, impl: str) -> None:
+        """Choose the prompt-phase attention behind the reference layer's `flash_attn_varlen_func(...)` call (llama_w4a8_unpad.py:232-242):
+        "flash_attn" = the third-party package as imported by the reference, "qserve_b200" = this repo's tcgen05 kernel.  The reference
+        source is not touched: the module-level name it calls through is rebound."""
+        from qserve_b200 import backend
+
+        assert impl in ("flash_attn", "qserve_b200")
+        self.mod.flash_attn_varlen_func = backend.flash_attn_varlen_func if impl == "qserve_b200" else self._flash_attn
 
     # -----------------------------------------------------------------------------------------------------------
     def _share_weights(self) -> None:

@@ -30,6 +30,9 @@ def main(path):
         for k in KEYS:
             if k in d and d[k] not in ("", "n/a"):
                 print(f"  {k:78s} {d[k]:>16s} {u.get(k, '')}")
+        for k in hdr:  # every tensor-pipe activity metric the report has (imma for the INT8 GEMMs, hmma for the fp16 attention)
+            if "pipe_tensor" in k and k not in KEYS and d[k] not in ("", "n/a", "0"):
+                print(f"  {k:78s} {d[k]:>16s} {u.get(k, '')}")
         stalls = sorted(((float(d[k]), k[len(STALL):].replace("_per_issue_active.ratio", "")) for k in hdr
                          if k.startswith(STALL) and k.endswith("_per_issue_active.ratio") and d[k] not in ("", "n/a")), reverse=True)
         print("  warp stall reasons (warps stalled per issue-active cycle):")
