@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--tp-layers", type=int, default=None, help="debug only")
     ap.add_argument("--tp-only", action="store_true", help="print only the tensor-parallel record (tuning runs)")
     ap.add_argument("--tp-allreduce", default="peer", choices=["peer", "nccl"], help="TP record: all-reduce fused into add+norm+quant over peer memory, or NCCL")
+    ap.add_argument("--tp-timeout", type=float, default=420.0, help="N > 1: seconds after which the tensor-parallel side record is abandoned (the headline line is still printed)")
     ap.add_argument("--tp-exact", action="store_true", help="TP record with the bit-exact parity rule (global per-token amax) instead of the throughput mode")
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
@@ -742,17 +743,63 @@ def main():
     del run
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
+    fused = not args.no_fused
+    clocks = clk.summary()
+
+    def make_line(tp_rec):
+        """The result line (rank 0).  Built from the data-parallel measurement alone, so that a failure of the tensor-parallel side record at
+        N > 1 can still be reported next to a valid headline."""
+        roof = roofline_from(kern, hbm_gbs, peak_src, fused)
+        sb = step_bytes(cfg, args.precision, args.batch, args.ctx, args.layers)
+        line = {
+            "metric": metric_name(args), "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s8", "data": "synthetic", "config": make_config(args, world),
+            "run": {"graph": not args.no_graph, "pdl": not args.no_pdl, "fused_small_ops": fused,
+                    "timing": "CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": args.batch * 8 * world, "d2h_bytes_per_step": args.batch * 8 * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": kern,
+            "step_hbm_frac": (sb / (ms_dev / args.steps * 1e-3)) / 1e9 / hbm_gbs,
+        }
+        if tp_rec is not None:
+            line["tp"] = tp_rec
+        return line
+
     tp_rec = None
     if not args.no_tp and (args.model, args.precision) == ("llama-3-8b", "w4a8kv4"):
+        import threading
+
+        tp_done = threading.Event()
+
+        def bail(why):
+            # N > 1 and the tensor-parallel record failed or hangs on some rank: the data-parallel headline is complete and valid -- print it with
+            # the error and leave without touching the (possibly wedged) communicator again
+            if rank == 0:
+                print(json.dumps(make_line({"error": why})), flush=True)
+            sys.stdout.flush()
+            os._exit(0)
+
+        def watchdog():
+            if not tp_done.wait(args.tp_timeout):
+                bail(f"tensor-parallel record did not finish within {args.tp_timeout} s")
+
         if world > 1:
             dist.barrier()  # rank 0 has just spent seconds on the kernel table: enter the collective phase together
+            threading.Thread(target=watchdog, daemon=True).start()
         try:
             with torch.no_grad():
                 tp_rec = tp_block(args, rank, world, dev, hbm_gbs)
         except Exception as e:  # noqa: BLE001
             tp_rec = {"error": repr(e)}
             if world > 1:
-                raise
+                if rank != 0:
+                    time.sleep(5)  # give rank 0 a moment to fail on its own (it prints); otherwise its watchdog prints
+                bail(repr(e)[:400])
+        tp_done.set()
 
     def finish():
         # do not let a slow communicator teardown keep the launcher alive after the result line is out
@@ -794,25 +841,7 @@ def main():
                "sample": f"3 timed runs (after 1 warm-up) of 1 of {cfg.layers} decoder layers (4 W4A8 GEMMs M={args.batch} + KV4 attention B={args.batch} ctx={args.ctx}) on "
                          f"torch-CPU dequant-then-matmul + fp16 lm_head once, extrapolated x{cfg.layers}; {layer_s:.2f} s/layer, lm_head {t_lm:.2f} s"}
 
-    fused = not args.no_fused
-    roof = roofline_from(kern, hbm_gbs, peak_src, fused)
-    sb = step_bytes(cfg, args.precision, args.batch, args.ctx, args.layers)
-    line = {
-        "metric": metric_name(args), "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "s8", "data": "synthetic", "config": make_config(args, world),
-        "run": {"graph": not args.no_graph, "pdl": not args.no_pdl, "fused_small_ops": fused,
-                "timing": "CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"},
-        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": args.batch * 8 * world, "d2h_bytes_per_step": args.batch * 8 * world,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches_per_step * args.steps,
-        "clocks": clk.summary(),
-        "roofline": roof,
-        "kernels": kern,
-        "step_hbm_frac": (sb / (ms_dev / args.steps * 1e-3)) / 1e9 / hbm_gbs,
-    }
-    if tp_rec is not None:
-        line["tp"] = tp_rec
+    line = make_line(tp_rec)
     if refm is not None:
         line["refmodel"] = refm
     if ref_gpu is not None:

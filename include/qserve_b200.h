@@ -81,8 +81,8 @@ QS_API int qs_w8a8_gemm(const int8_t* in_feats, const int8_t* kernel, const void
 QS_API size_t qs_gemm_workspace_bytes(void);
 /* test hook: force the cluster split-K factor (1, 2, 4 or 8) of the next GEMM calls; 0 = automatic */
 QS_API int qs_gemm_force_split(int split);
-/* test / tuning hook: force the tokens-per-tile of the GEMMs (32, 64, 128, 256; 0 = automatic; -1 = band-partitioned
- * one-CTA-per-SM kernel for wide per-channel layers at decode size); returns the previous value */
+/* test / tuning hook: force the tokens-per-tile of the GEMMs (32, 64, 128; 0 = automatic: 32 / 64 / 128 by M, and CTA-pair
+ * 256-token tiles (cta_group::2) for W4A8 at M >= 512); returns the previous value */
 QS_API int qs_gemm_force_tile_tokens(int nt);
 /* profiling hook: device buffer of 16 x uint64 per CTA receiving %globaltimer stamps of the GEMM phases; NULL disables */
 QS_API int qs_gemm_set_profile_buffer(void* dev_buffer);

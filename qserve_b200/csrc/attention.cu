@@ -748,7 +748,9 @@ decode_attention_kernel(const __half* __restrict__ q_in, const __half* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: prefill RoPE + KV quantise + page append: one warp per (token, query head)
+// K2: prefill RoPE + KV quantise + page append: one warp per (token, KV head): it rotates the G query heads of the group and the key head with
+//     ONE evaluation of the position's sines / cosines (the first version, one warp per query head, spent its time in 32 redundant
+//     powf / sincosf per token: 365 us per layer for the 8 x 1024-token prompt batch), then quantises and appends K and V.
 //     applyBiasRopeUpdateKVCache.h:94-455 (STORE_QKV = true, no bias, NeoX)
 // ------------------------------------------------------------------------------------------------
 template <int BITS>
@@ -761,53 +763,53 @@ __global__ void __launch_bounds__(128) prefill_append_kernel(__half* __restrict_
   const int lane = threadIdx.x & 31;
   const int G = num_heads / num_kv_heads;
   const int warps_per_cta = blockDim.x >> 5;
-  const long long n_work = static_cast<long long>(num_tokens) * num_heads;
+  const long long n_work = static_cast<long long>(num_tokens) * num_kv_heads;
   const int n = (num_heads + 2 * num_kv_heads) * kD;
   const int half_rot = rotary_dim / 2;
   for (long long wi = static_cast<long long>(blockIdx.x) * warps_per_cta + (threadIdx.x >> 5); wi < n_work;
        wi += static_cast<long long>(gridDim.x) * warps_per_cta) {
-    const int token = static_cast<int>(wi / num_heads), head = static_cast<int>(wi - static_cast<long long>(token) * num_heads);
-    const int kvh = head / G;
+    const int token = static_cast<int>(wi / num_kv_heads), kvh = static_cast<int>(wi - static_cast<long long>(token) * num_kv_heads);
     const int gtok = token + (padding_offset ? padding_offset[token] : 0);
     const int bidx = gtok / seq_len, pos = gtok - bidx * seq_len;
     const int len = seq_lens[bidx];
     if (pos >= len) continue;  // padded slot (cannot happen with un-padded inputs)
-    __half* qrow = qkv + static_cast<size_t>(token) * n + static_cast<size_t>(head) * kD;
-    __half* krow = qkv + static_cast<size_t>(token) * n + static_cast<size_t>(num_heads + kvh) * kD;
-    __half* vrow = qkv + static_cast<size_t>(token) * n + static_cast<size_t>(num_heads + num_kv_heads + kvh) * kD;
-    const bool kv_writer = (head == kvh * G);
-    // lane handles rotary pairs i = 2*lane, 2*lane+1  (i in [0, 64)) -> dims i and i + half_rot
-    float kx[4];  // rotated k: dims 2l, 2l+1, 64+2l, 65+2l
-    float vx[4];
+    __half* trow = qkv + static_cast<size_t>(token) * n;
+    // lane handles rotary pairs i = 2*lane, 2*lane+1  (i in [0, 64)) -> dims i and i + half_rot: one half2 at each end
+    float cs[2], sn[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int i = 2 * lane + e;
-      float cs, sn;
-      const bool rot = true;  // rotary_dim == head_dim (update_kv_cache.cu:54)
       const float inv_freq = __fdiv_rn(static_cast<float>(pos), powf(rotary_base, __fdiv_rn(static_cast<float>(2 * i), static_cast<float>(rotary_dim))));
-      sincosf(inv_freq, &sn, &cs);
-      const int i1 = i + half_rot;
-      const float q0 = __half2float(qrow[i]), q1 = __half2float(qrow[i1]);
-      if (rot) {
-        qrow[i] = __float2half_rn(__fsub_rn(__fmul_rn(cs, q0), __fmul_rn(sn, q1)));
-        qrow[i1] = __float2half_rn(__fadd_rn(__fmul_rn(cs, q1), __fmul_rn(sn, q0)));
-      }
-      if (kv_writer) {
-        const float k0 = __half2float(krow[i]), k1 = __half2float(krow[i1]);
-        __half r0 = krow[i], r1 = krow[i1];
-        if (rot) {
-          r0 = __float2half_rn(__fsub_rn(__fmul_rn(cs, k0), __fmul_rn(sn, k1)));
-          r1 = __float2half_rn(__fadd_rn(__fmul_rn(cs, k1), __fmul_rn(sn, k0)));
-          krow[i] = r0;
-          krow[i1] = r1;
-        }
-        kx[e] = __half2float(r0);
-        kx[2 + e] = __half2float(r1);
-        vx[e] = __half2float(vrow[i]);
-        vx[2 + e] = __half2float(vrow[i1]);
-      }
+      sincosf(inv_freq, &sn[e], &cs[e]);
     }
-    if (!kv_writer || kv_pointers == nullptr) continue;
+    auto rotate = [&](__half* row, float (&lo)[2], float (&hi)[2]) {  // in place; returns the rotated values (rounded to fp16) as floats
+      __half2* p0 = reinterpret_cast<__half2*>(row + 2 * lane);
+      __half2* p1 = reinterpret_cast<__half2*>(row + half_rot + 2 * lane);
+      const float2 a = __half22float2(*p0), b = __half22float2(*p1);
+      const float x0[2] = {a.x, a.y}, x1[2] = {b.x, b.y};
+      __half r0[2], r1[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        r0[e] = __float2half_rn(__fsub_rn(__fmul_rn(cs[e], x0[e]), __fmul_rn(sn[e], x1[e])));
+        r1[e] = __float2half_rn(__fadd_rn(__fmul_rn(cs[e], x1[e]), __fmul_rn(sn[e], x0[e])));
+        lo[e] = __half2float(r0[e]);
+        hi[e] = __half2float(r1[e]);
+      }
+      *p0 = __halves2half2(r0[0], r0[1]);
+      *p1 = __halves2half2(r1[0], r1[1]);
+    };
+    float t0[2], t1[2];
+    for (int g = 0; g < G; ++g) rotate(trow + static_cast<size_t>(kvh * G + g) * kD, t0, t1);
+    float kx[4], vx[4];  // dims 2l, 2l+1, 64+2l, 65+2l
+    rotate(trow + static_cast<size_t>(num_heads + kvh) * kD, t0, t1);
+    kx[0] = t0[0]; kx[1] = t0[1]; kx[2] = t1[0]; kx[3] = t1[1];
+    {
+      const __half* vrow = trow + static_cast<size_t>(num_heads + num_kv_heads + kvh) * kD;
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(vrow + 2 * lane));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(vrow + half_rot + 2 * lane));
+      vx[0] = a.x; vx[1] = a.y; vx[2] = b.x; vx[3] = b.y;
+    }
+    if (kv_pointers == nullptr) continue;
     if (pos < max(len - max_positions, 0)) continue;  // outside the cyclic window (:268-271)
     const int blk = pos / pg.tokens_per_block, slot = pos - blk * pg.tokens_per_block;
     const float L = (BITS == 4) ? 15.f : 255.f;
@@ -972,9 +974,9 @@ int prefill_rope_append(const PrefillAppendArgs& a) {
   const int bits = a.int4_kv ? 4 : 8;
   QS_REQUIRE(a.size_per_token == a.num_kv_heads * kD * bits / 8, "apply_bias_rope_update_kv_cache: size_per_token=%d does not match", a.size_per_token);
   PageGeom pg{a.tokens_per_block, a.tokens_per_block * a.size_per_token, a.num_kv_heads};
-  const long long work = static_cast<long long>(a.num_tokens) * a.num_heads;
+  const long long work = static_cast<long long>(a.num_tokens) * a.num_kv_heads;  // one warp per (token, KV head)
   long long blocks = (work + 3) / 4;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > static_cast<long long>(num_sms()) * 16) blocks = static_cast<long long>(num_sms()) * 16;
   auto run = [&](auto kern) {
     return launch_pdl(kern, dim3(static_cast<unsigned>(blocks)), dim3(128), 0, a.stream, "apply_bias_rope_update_kv_cache", static_cast<__half*>(a.qkv),
                       a.seq_lens, a.padding_offset, a.kv_pointers, a.num_tokens, a.max_blocks, a.num_heads, a.num_kv_heads, a.seq_len, pg,

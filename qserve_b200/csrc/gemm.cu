@@ -578,7 +578,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   uint64_t* bar_wempty = bar_wfull + WS;
   uint64_t* bar_xfull = bar_wempty + WS;    // leader only: BOTH halves of the activation stage have landed (the peer's TMA signals it remotely)
   uint64_t* bar_xempty = bar_xfull + AS;    // MMA commit (multicast) -> this CTA's activation producer
-  uint64_t* bar_afull = bar_xempty + AS;    // leader only: 8 arrivals = the four unpack warps of both CTAs
+  uint64_t* bar_afull = bar_xempty + AS;    // leader only: 16 arrivals = the eight unpack warps of both CTAs
   uint64_t* bar_aempty = bar_afull + TA;    // MMA commit (multicast) -> this CTA's unpack warps
   uint64_t* bar_dfull = bar_aempty + TA;    // both MMA issuers' last commits of a tile (multicast): accumulators complete
   uint64_t* bar_zero = bar_dfull + 1;       // leader only: accumulators of both CTAs drained and zero-filled (16 arrivals: 8 epilogue warps each)
@@ -599,9 +599,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_act);
     tma_prefetch_desc(&tmap_w);
-    for (int i = 0; i < WS; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 4); }
+    for (int i = 0; i < WS; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 8); }
     for (int i = 0; i < AS; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
-    for (int i = 0; i < TA; ++i) { mbar_init(&bar_afull[i], 8); mbar_init(&bar_aempty[i], 1); }
+    for (int i = 0; i < TA; ++i) { mbar_init(&bar_afull[i], 16); mbar_init(&bar_aempty[i], 1); }
     mbar_init(bar_dfull, 2);
     mbar_init(bar_zero, 16);
     fence_barrier_init();
@@ -707,10 +707,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       }
     }
   } else if ((warp >= 2 && warp <= 5) || warp >= 8) {
-    // ===================================== unpack (warps 2..5) + epilogue (warps 2..5 and 8..11), both CTAs =====================================
-    // A warp reaches the TMEM lanes 32 * (warp % 4) ..: warps w and w + 4 (mod 4 equal) share a lane quadrant and split the 256 token columns.
-    const bool unpacker = warp < 8;
+    // ===================================== unpack + epilogue: warps 2..5 and 8..11, both CTAs =====================================
+    // A warp reaches the TMEM lanes 32 * (warp % 4) ..: the two warps of a lane quadrant split every stage's two 128-K sub-blocks (unpack) and the
+    // 256 token columns (epilogue).  (Per-group mode is bound by the integer work of the level-2 dequantisation in this loop: 4 -> 8 warps.)
+    const bool unpacker = warp < 8;           // first / second warp of its lane quadrant
     const int quad = warp & 3;
+    const int usel = unpacker ? 0 : 1;        // the 128-K sub-block of a stage this warp unpacks
     const int col0 = unpacker ? 0 : NT / 2;   // first accumulator column (token) of this warp's half
     const int epi_tid = quad * 32 + lane;     // channel inside the tile
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -730,13 +732,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     uint32_t ph = 0, pha = 0;
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int m_tile = tile_m(lt), n_tile = tile_n(lt);
-      if (unpacker) {
+      {
         for (int it = 0; it < n_kb; ++it) {
           mbar_wait(&bar_wfull[s], ph);
           mbar_wait(&bar_aempty[ta], pha ^ 1);
           tc_fence_after();
-#pragma unroll
-          for (int u = 0; u < kSub; ++u) {
+          static_assert(kSub == 2, "two warps per lane quadrant take one sub-block each");
+          {
+            const int u = usel;
             const uint8_t* wsrc = s_w + s * C::kWBytes + u * C::kWSub + quad * 2048 + lane * 16;
             const uint32_t tdst = trow + NT + ta * C::kAStageCols + u * (kBK / 4);
             uint32_t sc4 = 0, zp4 = 0;

@@ -8,6 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import qserve_backend.qgemm_w4a8_per_chn as op  # noqa: E402
+import qserve_backend.qgemm_w4a8_per_group as opg  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 if os.environ.get("QS_FORCE_NT"):  # tile-size A/B: tokens per tile (32 / 64 / 128 / 256)
@@ -21,6 +22,15 @@ w = torch.randint(-128, 128, (N, K // 2), dtype=torch.int8, generator=g).to(dev)
 s1 = torch.full((N,), 0.01, dtype=torch.half, device=dev)
 sa = torch.full((M,), 0.01, dtype=torch.half, device=dev)
 out = torch.empty((M, N), dtype=torch.half, device=dev)
+if os.environ.get("QS_G128"):  # the per-group (g128) kernel on the same shape
+    z2 = torch.randint(-100, 0, (K // 128, N), dtype=torch.int8, generator=g).to(dev)
+    s2 = torch.randint(1, 9, (K // 128, N), dtype=torch.int8, generator=g).to(dev)
+    _chn = op.gemm_forward_cuda
+
+    class op:  # noqa: N801
+        @staticmethod
+        def gemm_forward_cuda(a, w, s1, sa, _z, _s, out):
+            opg.gemm_forward_cuda(a, w, z2, s2, s1, sa, out)
 for _ in range(4):
     op.gemm_forward_cuda(a, w, s1, sa, s1, sa, out)
 torch.cuda.synchronize()
