@@ -165,7 +165,8 @@ class DecodeRunner:
         self.max_seq_len = ctx + 1
 
         # ---- persistent ActivationBuffer (input_metadata.py:71-109; aliasing kept) ------------------------------
-        self.act_buffer = torch.empty(M * max(self.q_size + 2 * self.kv_size, 2 * self.Iloc), dtype=torch.half, device=dev)
+        # (H is in the max for tensor parallelism: at TP = 8 a 72B model's sharded qkv / gate_up rows are narrower than the full hidden row of out_buf)
+        self.act_buffer = torch.empty(M * max(self.q_size + 2 * self.kv_size, 2 * self.Iloc, H), dtype=torch.half, device=dev)
         self.qkv_buf = self.act_buffer[: M * (self.q_size + 2 * self.kv_size)].view(M, -1)
         self.out_buf = self.act_buffer[: M * H].view(M, H)
         self.gate_up_buf = self.act_buffer[: M * 2 * self.Iloc].view(M, -1)

@@ -41,6 +41,29 @@ def test_hidden_state_is_finite(dev):
     assert torch.isfinite(run.out_buf.float()).all()
 
 
+@pytest.mark.parametrize("tp_size", [4, 8])
+def test_one_rank_of_a_tensor_parallel_72b_layer_runs(dev, tp_size):
+    """BASELINE config 5 shapes on ONE GPU: rank 3's shard of a Qwen1.5-72B layer at TP = 4 / 8 without the collectives (`no_comm`).  At TP = 8 the
+    sharded qkv (3072) and gate_up (6144) rows are NARROWER than the hidden row (8192): the activation buffer must be sized by the widest of the three
+    (the first 8-GPU run of the bench died here).  Fused graph path and reference op sequence, finite outputs."""
+    from qserve_b200.decode import DecodeRunner
+
+    for fused in (True, False):
+        run = DecodeRunner("qwen1.5-72b", "w4a8kv4", batch=8, ctx=130, device=dev, layers=1, seed=5, tp_rank=3, tp_size=tp_size, no_comm=True, fused=fused)
+        with torch.no_grad():
+            tok = run.forward(run.tokens_in).clone()
+        if fused:
+            run.capture()
+            run.step()
+            torch.cuda.synchronize()
+            assert torch.equal(tok, run.tokens_out)
+        torch.cuda.synchronize()
+        assert tok.shape == (8,) and int(tok.min()) >= 0 and int(tok.max()) < run.cfg.vocab
+        assert torch.isfinite(run.out_buf.float()).all()
+        del run
+        torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("precision,group", [("w4a8kv4", -1), ("w4a8kv4-g128", 128)])
 def test_converted_checkpoint_loads_and_runs(dev, precision, group):
     """fake-quant checkpoint -> convert -> fuse -> load_into_runner -> the runner's qkv GEMM equals the oracle GEMM on the

@@ -1,0 +1,5 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+O=gpurun_out
+python -c "import qserve_backend" 2>/dev/null || python -m qserve_b200.build > $O/r2_rebuild.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_decode_runner.py tests/test_gpu_elementwise.py -m gpu -q -x 2>&1 | grep -v Warning | tail -15 > $O/r2_tests36.log
