@@ -119,7 +119,8 @@ QS_API int qs_apply_bias_rope_update_kv_cache(void* qkv, const int32_t* seq_lens
  *   max_seqlen, dropout_p=0.0, causal=True) at qserve/modeling/models/llama_w4a8_unpad.py:232-242.
  *   q [T,Hq,128], k / v [T,Hkv,128] fp16: strided views of the qkv buffer apply_bias_rope_update_kv_cache has rotated in place (row strides in
  *   halfs, multiples of 8); cu_seqlens int32 [batch+1] shared by queries and keys; out fp16 [T,Hq,128].  Causal, no dropout, GQA by
- *   Hq / Hkv.  fp32 softmax, P rounded to fp16 before the second MMA (as flash-attn does); tcgen05 kind::f16, sm_100a only.              */
+ *   Hq / Hkv.  fp32 softmax, P rounded to fp16 before the second MMA (as flash-attn does); tcgen05 kind::f16, sm_100a only.
+ *   max_seqlen must be >= the longest sequence (as for flash-attn: query blocks beyond it are not launched).                          */
 QS_API int qs_prefill_attention(const void* q, const void* k, const void* v, int64_t q_stride, int64_t k_stride, int64_t v_stride, void* out,
                          int64_t out_stride, const int32_t* cu_seqlens, int batch, int num_tokens, int max_seqlen, int num_heads,
                          int num_kv_heads, int head_dim, float softmax_scale, void* stream);

@@ -45,6 +45,10 @@ constexpr int kBM = 128;  // output channels per tile (UMMA M)
 constexpr int kBK = 128;  // K sub-block (= one g128 group, one 128-byte swizzled activation row)
 constexpr int kSub = 2;    // sub-blocks per pipeline stage: per-stage barrier latencies are amortised over 256 K
 constexpr int kNumThreads = 256;
+#ifndef QS_PAIR_CVT
+#define QS_PAIR_CVT 1
+#endif
+constexpr bool kPairCvt = QS_PAIR_CVT != 0;
 constexpr int kPairThreads = 384;  // gemm_pair_kernel: the 8 warps of gemm_kernel + 4 more epilogue warps
 // warp roles: 0 weight producer | 1 TMEM owner + MMA issuer (even stages) | 2..5 unpack + TMEM epilogue | 6 activation producer |
 // 7 MMA issuer (odd stages).
@@ -145,10 +149,12 @@ __device__ __forceinline__ float int2float_rn_noxu(int32_t v) {
 template <int V>
 struct IntTag { static constexpr int value = V; };
 
-template <int MODE>
+// CVT = true: the conversion instruction itself (cvt.rn.f32.s32; 2.5 cycles per warp instruction measured, profiles/r01_ubench_pipes.txt) instead of the
+// five-instruction emulation -- same value; used where the epilogue is instruction-issue bound (the prefill pair kernel: 256 outputs per thread).
+template <int MODE, bool CVT = false>
 __device__ __forceinline__ float epilogue_one(int32_t acc, float ws, float wsz, float as, float asum) {
   // IEEE fp32, reference source order, no FMA contraction (bit-exact against oracle/w4a8.py)
-  float ps = int2float_rn_noxu(acc);
+  float ps = CVT ? __int2float_rn(acc) : int2float_rn_noxu(acc);
   if constexpr (MODE == kModeW4Chn) {
     // w4a8_per_chn/gemm_cuda.cu:586  psum * wscale * ascale - w_sz * a_ssum
     float t = __fmul_rn(__fmul_rn(ps, ws), as);
@@ -825,7 +831,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float o = epilogue_one<MODE>(static_cast<int32_t>(r[i]), ws, wz, as[i], am[i]);
+            const float o = epilogue_one<MODE, kPairCvt>(static_cast<int32_t>(r[i]), ws, wz, as[i], am[i]);
             out[static_cast<size_t>(i) * p.N] = __float2half_rn(o);
             if constexpr (ACC) p.acc_out[static_cast<size_t>(m0 + tok0 + i) * p.N + n] = static_cast<int32_t>(r[i]);
           }
@@ -833,7 +839,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) {  // (fully unrolled: a dynamic index would push r[] into local memory for the fast path as well)
             if (tok0 + i < tok_end) {
-              const float o = epilogue_one<MODE>(static_cast<int32_t>(r[i]), ws, wz, s_asc[tok0 + i], s_asum[tok0 + i]);
+              const float o = epilogue_one<MODE, kPairCvt>(static_cast<int32_t>(r[i]), ws, wz, s_asc[tok0 + i], s_asum[tok0 + i]);
               out[static_cast<size_t>(i) * p.N] = __float2half_rn(o);
               if constexpr (ACC) p.acc_out[static_cast<size_t>(m0 + tok0 + i) * p.N + n] = static_cast<int32_t>(r[i]);
             }

@@ -95,15 +95,6 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-
 struct PrefillAttnParams {
   const int* cu_seqlens;  // [B + 1]
   __half* out;            // [T, Hq * 128] rows of out_stride halfs
@@ -360,6 +351,7 @@ int prefill_attention(const PrefillAttnArgs& a) {
   QS_REQUIRE(a.num_heads > 0 && a.num_kv_heads > 0 && a.num_heads % a.num_kv_heads == 0, "prefill_attention: heads=%d kv_heads=%d", a.num_heads, a.num_kv_heads);
   QS_REQUIRE(a.batch >= 0 && a.num_tokens >= 0 && a.max_seqlen >= 0, "prefill_attention: negative size");
   if (a.batch == 0 || a.num_tokens == 0 || a.max_seqlen == 0) return QS_OK;
+  QS_REQUIRE(a.batch <= 65535 && a.num_heads <= 65535, "prefill_attention: batch=%d / heads=%d exceed the grid limits", a.batch, a.num_heads);
   QS_REQUIRE(a.q && a.k && a.v && a.out && a.cu_seqlens, "prefill_attention: null pointer");
   QS_REQUIRE(a.q_stride % 8 == 0 && a.k_stride % 8 == 0 && a.v_stride % 8 == 0 && a.out_stride % 8 == 0, "prefill_attention: row strides must be multiples of 8 halfs");
   QS_REQUIRE(((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) | reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.out)) & 15) == 0,
