@@ -49,6 +49,10 @@ constexpr int kNumThreads = 256;
 #define QS_PAIR_CVT 1
 #endif
 constexpr bool kPairCvt = QS_PAIR_CVT != 0;
+#ifndef QS_DECODE_CVT
+#define QS_DECODE_CVT 1
+#endif
+constexpr bool kDecodeCvt = QS_DECODE_CVT != 0;  // the same choice for the epilogue of gemm_kernel (A/B: profiles/r02_notes.md 4b)
 constexpr int kPairThreads = 384;  // gemm_pair_kernel: the 8 warps of gemm_kernel + 4 more epilogue warps
 // warp roles: 0 weight producer | 1 TMEM owner + MMA issuer (even stages) | 2..5 unpack + TMEM epilogue | 6 activation producer |
 // 7 MMA issuer (odd stages).
@@ -136,9 +140,11 @@ __device__ __forceinline__ void st_dsmem_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// INT32 -> FP32, round to nearest even, WITHOUT the conversion unit (I2F issues once per 16 cycles per SM sub-partition on the
-// XU pipe, and the epilogue needs one per output):  v = hi * 65536 + lo, both halves are converted exactly by the 1.5 * 2^23
-// magic-number add, and the single rounding of the fused multiply-add equals cvt.rn.f32.s32(v).
+// INT32 -> FP32, round to nearest even, without the conversion instruction:  v = hi * 65536 + lo, both halves are converted exactly by the
+// 1.5 * 2^23 magic-number add, and the single rounding of the fused multiply-add equals cvt.rn.f32.s32(v).  Round 1 used it in every epilogue
+// on the assumption that I2F is a quarter-rate XU instruction; the pipe micro-benchmark (profiles/r01_ubench_pipes.txt: 2.5 cycles per warp
+// instruction, against 5 x ~2 for this sequence) and the A/B of round 2 say otherwise (decode step 2.797 -> 2.771 ms, prefill tiles +2 %), so the
+// kernels now convert with the instruction; this stays as the -DQS_DECODE_CVT=0 / -DQS_PAIR_CVT=0 variant.
 __device__ __forceinline__ float int2float_rn_noxu(int32_t v) {
   const int32_t hi = v >> 16, lo = v & 0xFFFF;
   const float fhi = __fsub_rn(__int_as_float(0x4B400000 + hi), 12582912.f);
@@ -149,8 +155,7 @@ __device__ __forceinline__ float int2float_rn_noxu(int32_t v) {
 template <int V>
 struct IntTag { static constexpr int value = V; };
 
-// CVT = true: the conversion instruction itself (cvt.rn.f32.s32; 2.5 cycles per warp instruction measured, profiles/r01_ubench_pipes.txt) instead of the
-// five-instruction emulation -- same value; used where the epilogue is instruction-issue bound (the prefill pair kernel: 256 outputs per thread).
+// CVT = true: cvt.rn.f32.s32 itself instead of the five-instruction emulation above -- same value.
 template <int MODE, bool CVT = false>
 __device__ __forceinline__ float epilogue_one(int32_t acc, float ws, float wsz, float as, float asum) {
   // IEEE fp32, reference source order, no FMA contraction (bit-exact against oracle/w4a8.py)
@@ -465,8 +470,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant_
     const size_t ostep = static_cast<size_t>(tstep) * p.N;
     auto finish = [&](int tok, int2 acc, __half* dst) {
       const float as = s_asc[tok], asum = s_asum[tok];
-      const float o0 = epilogue_one<MODE>(acc.x, ws0, wz0, as, asum);
-      const float o1 = epilogue_one<MODE>(acc.y, ws1, wz1, as, asum);
+      const float o0 = epilogue_one<MODE, kDecodeCvt>(acc.x, ws0, wz0, as, asum);
+      const float o1 = epilogue_one<MODE, kDecodeCvt>(acc.y, ws1, wz1, as, asum);
       *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(o0, o1);  // one packed conversion, each half rounded to nearest even
       if constexpr (ACC) *reinterpret_cast<int2*>(p.acc_out + (dst - p.out)) = acc;
     };
