@@ -1083,8 +1083,14 @@ int dispatch_gemm(const GemmArgs& a) {
   constexpr bool w8 = (MODE == kModeW8), grp = (MODE == kModeW4Grp);
   QS_REQUIRE(a.force_nt == 0 || a.force_nt == 32 || a.force_nt == 64 || a.force_nt == 128, "gemm: tile tokens must be 32, 64 or 128");
   if constexpr (MODE != kModeW8) {
-    static const bool no_pair = getenv("QS_GEMM_NO_PAIR") != nullptr;  // A/B hook
-    if (!no_pair && a.force_nt == 0 && a.force_split == 0 && a.M >= 512 && (a.N / kBM) % 2 == 0 && a.K >= 512) return launch_gemm_pair<MODE>(a);
+    static const bool no_pair = getenv("QS_GEMM_NO_PAIR") != nullptr;  // A/B hooks
+    static const int pair_min_m = getenv("QS_GEMM_PAIR_MIN_M") ? atoi(getenv("QS_GEMM_PAIR_MIN_M")) : 512;
+    // Below 512 tokens the pair kernel pays only if its 256-token tiles are as well filled as the 128-token ones (an even number of 128-token
+    // tiles: M in (128, 256] or (384, 512)) and there is at least one pair tile per TPC (measured, profiles/r02_notes.md 4b: gate_up at M = 256
+    // 30.4 vs 35.5 us, at M = 320 58.1 vs 50.5; o_proj (16 pair tiles) at M = 256 16.6 vs 12.0)
+    const int t128 = (a.M + 127) / 128;
+    const bool small_ok = a.M > 128 && t128 % 2 == 0 && (a.N / kBM / 2) * ((a.M + 255) / 256) >= num_sms() / 2;
+    if (!no_pair && a.force_nt == 0 && a.force_split == 0 && (a.M >= pair_min_m || small_ok) && (a.N / kBM) % 2 == 0 && a.K >= 512) return launch_gemm_pair<MODE>(a);
   }
   int nt = a.force_nt > 0 ? a.force_nt : 0;
   if (nt == 0) {

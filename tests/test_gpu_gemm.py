@@ -36,9 +36,12 @@ def _report(name, acc_g, acc_o, out_g, out_o):
 SHAPES = [  # (M, N, K)
     (16, 128, 128), (1, 256, 256), (16, 4096, 4096), (33, 384, 512), (64, 256, 1024), (64, 4096, 4096),
     (100, 512, 640), (128, 256, 256), (200, 384, 384), (256, 256, 512), (300, 256, 256), (700, 384, 256),
-    # prefill tiles (256 tokens): an even number of channel tiles takes the multicast-pair path (two CTAs share each activation tile), an odd
-    # one the single-CTA path; ragged last token block, K % 256 == 128, many waves of clusters
+    # prefill tiles: M >= 512 with an even number of channel tiles takes the CTA-pair kernel (cta_group::2, 256-token tiles, persistent), an odd number or
+    # K < 512 the 128-token tiles; ragged last token block, K % 256 == 128, several tiles per persistent pair
     (1000, 512, 1152), (513, 1024, 384), (2048, 768, 512),
+    # 128 < M < 512 takes the pair kernel only when its 256-token tiles are well filled AND there is a pair tile per TPC (wide layers):
+    # one partial 256-token tile (192 tokens), two tiles with a ragged second one (448)
+    (192, 19200, 512), (448, 9728, 640),
 ]
 
 

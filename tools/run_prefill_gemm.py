@@ -14,7 +14,7 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 if os.environ.get("QS_FORCE_NT"):  # tile-size A/B: tokens per tile (32 / 64 / 128 / 256)
     from qserve_b200._lib import lib
     lib.qs_gemm_force_tile_tokens(int(os.environ["QS_FORCE_NT"]))
-N, K = 28672, 4096
+N, K = int(os.environ.get("QS_N", 28672)), int(os.environ.get("QS_K", 4096))
 dev = torch.device("cuda:0")
 g = torch.Generator(device="cpu").manual_seed(0)
 a = torch.randint(-127, 128, (M, K), dtype=torch.int8, generator=g).to(dev)
