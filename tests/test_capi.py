@@ -54,6 +54,20 @@ def test_dropin_module_surface():
     assert len(inspect.signature(qb.fused_attention.apply_bias_rope_update_kv_cache).parameters) == 15
 
 
+def test_prompt_attention_has_the_call_site_signature():
+    """`backend.flash_attn_varlen_func` stands in for flash_attn.flash_attn_varlen_func at llama_w4a8_unpad.py:232-242, which passes q, k, v
+    positionally and cu_seqlens_q / cu_seqlens_k / max_seqlen_q / max_seqlen_k / dropout_p / causal by keyword: same names, same positional order
+    as flash-attn 2.x for the leading parameters; CPU tensors are rejected like everywhere else."""
+    from qserve_b200 import backend
+
+    params = list(inspect.signature(backend.flash_attn_varlen_func).parameters)
+    assert params[:10] == ["q", "k", "v", "cu_seqlens_q", "cu_seqlens_k", "max_seqlen_q", "max_seqlen_k", "dropout_p", "softmax_scale", "causal"]
+    q = torch.zeros(4, 2, 128, dtype=torch.half)
+    cu = torch.tensor([0, 4], dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        backend.flash_attn_varlen_func(q, q, q, cu_seqlens_q=cu, cu_seqlens_k=cu, max_seqlen_q=4, max_seqlen_k=4, dropout_p=0.0, causal=True)
+
+
 def test_no_cpu_fallback():
     """CPU tensors are rejected (the reference's CHECK_DEVICE); nothing silently computes on the host."""
     import qserve_backend as qb
